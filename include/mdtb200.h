@@ -1,0 +1,146 @@
+/*
+ * mdtb200.h -- C ABI of the B200-native MDT denoising hot path (libmdtb200.so).
+ *
+ * Drop-in boundary: everything below replaces the arithmetic behind the reference's
+ * Hydra-built score wrapper (paths relative to the reference repo root):
+ *
+ *   mdt/models/edm_diffusion/score_wrappers.py:18-100   GCDenoiser.{forward,loss,forward_context_only}
+ *   mdt/models/networks/mdtv_transformer.py:208-244     MDTVTransformer.{forward,forward_enc_only,forward_dec_only}
+ *   mdt/models/edm_diffusion/gc_sampling.py:164-210,256-311,699-733,922-951   sample_{euler,heun,dpmpp_2m,ddim}
+ *   mdt/models/mdtv_agent.py:523-550,593-658            denoise_actions / sample_loop (the caller)
+ *
+ * Conventions
+ *   - plain C types only: device/host pointers, sizes, a cudaStream_t passed as void*.
+ *   - all tensors fp32, contiguous, row-major; weights in nn.Linear layout (out, in).
+ *   - every function returns 0 on success, a negative MDTB200_E* code on failure and never
+ *     throws / exits; mdtb200_last_error() gives the message.  Asynchronous CUDA faults
+ *     surface at the caller's next synchronisation, as in PyTorch.
+ *   - input/output pointers are borrowed for the duration of the call only.  Weight pointers
+ *     are read by mdtb200_commit_weights() and not retained: the library keeps its own packed
+ *     copy (re-commit after load_state_dict / EMA swap / optimizer step).
+ *   - a handle is bound to the CUDA device that was current at mdtb200_create(); it is
+ *     re-entrant per handle, holds no global mutable state, and launches all work on the
+ *     stream passed in (sampling graphs are captured on a private stream and *launched* on
+ *     the caller's stream, so the legacy default stream is fine).
+ */
+#ifndef MDTB200_H_
+#define MDTB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDTB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MDTB200_API __attribute__((visibility("default")))
+#else
+#define MDTB200_API
+#endif
+
+enum {
+  MDTB200_OK = 0,
+  MDTB200_EINVAL = -1,     /* bad argument / shape / config */
+  MDTB200_ESTATE = -2,     /* call order violated (weights not committed, no context encoded, ...) */
+  MDTB200_ECUDA = -3,      /* CUDA runtime / driver error (message carries cudaGetErrorString) */
+  MDTB200_ENOMEM = -4,
+  MDTB200_EUNSUPPORTED = -5
+};
+
+/* score-network flavour: conf/model/model/mdtv_transformer.yaml vs mdt_transformer.yaml */
+enum { MDTB200_VARIANT_MDTV = 0, MDTB200_VARIANT_MDT = 1 };
+
+/* GEMM arithmetic.  FP32 = exact fp32 FMA on CUDA cores (reference-grade rounding).
+ * BF16X3 = tcgen05 tensor cores, each fp32 operand split into bf16 hi+lo, three MMAs
+ * (hi*hi + lo*hi + hi*lo) accumulated in fp32 TMEM: ~2^-17 relative operand error, meets
+ * the 1e-4 action tolerance.  BF16 = single-pass bf16 tensor cores (fast, ~1e-2 error:
+ * opt-in only, does NOT meet the parity tolerance). */
+enum { MDTB200_PREC_FP32 = 0, MDTB200_PREC_BF16X3 = 1, MDTB200_PREC_BF16 = 2 };
+
+/* fused samplers (gc_sampling.py) */
+enum { MDTB200_SAMPLER_DDIM = 0, MDTB200_SAMPLER_EULER = 1, MDTB200_SAMPLER_HEUN = 2, MDTB200_SAMPLER_DPMPP_2M = 3 };
+
+/* goal modality: selects lang_emb vs goal_emb (mdtv_transformer.py:268-273) */
+enum { MDTB200_MODALITY_VIS = 0, MDTB200_MODALITY_LANG = 1 };
+
+typedef struct MdtConfig {
+  int32_t abi_version;     /* = MDTB200_ABI_VERSION */
+  int32_t variant;         /* MDTB200_VARIANT_* */
+  int32_t embed_dim;       /* d: 384 (MDT-V) / 512 (MDT); multiple of 64 */
+  int32_t n_heads;         /* 8; head_dim = d / n_heads must be <= 64 and a multiple of 4 */
+  int32_t n_enc_layers;
+  int32_t n_dec_layers;
+  int32_t action_dim;      /* 7 */
+  int32_t action_seq_len;  /* T_a = 10 (<= 16) */
+  int32_t goal_dim;        /* 512 */
+  int32_t obs_dim;         /* 384 (MDT-V) / 512 (MDT) */
+  int32_t n_state_tokens;  /* MDT-V: obs_seq_len * n_obs_token = 3; MDT: 2 (static, gripper) */
+  int32_t precision;       /* MDTB200_PREC_* */
+  int32_t max_batch;       /* workspace is sized for this many samples per call */
+  float   sigma_data;      /* 0.5 */
+} MdtConfig;
+
+typedef struct MdtHandle MdtHandle;
+
+/* lifecycle ------------------------------------------------------------------------------ */
+MDTB200_API int         mdtb200_abi_version(void);
+MDTB200_API int         mdtb200_create(const MdtConfig* cfg, MdtHandle** out);
+MDTB200_API void        mdtb200_destroy(MdtHandle* h);
+/* message of the last failing call on this handle (h == NULL: last mdtb200_create failure) */
+MDTB200_API const char* mdtb200_last_error(const MdtHandle* h);
+
+/* weights: bind every tensor of the reference state dict by its key, e.g.
+ * "inner_model.decoder.blocks.0.attn.key.weight" (same names/order the reference's EMA zip
+ * relies on, mdt/models/mdtv_agent.py:152-158), then commit.  Unknown names are ignored
+ * (pos_emb / proprio_emb are unused at inference in MDT-V); missing ones fail the commit. */
+MDTB200_API int mdtb200_bind_weight(MdtHandle* h, const char* name, const float* dev_ptr, int64_t numel);
+MDTB200_API int mdtb200_commit_weights(MdtHandle* h, void* stream);
+
+/* forward_enc_only (mdtv_transformer.py:213-222): goal (B, goal_dim), state (B, n_state_tokens,
+ * obs_dim) [MDT: token 0 = static, token 1 = gripper].  Stores the context and the decoder's
+ * cross-attention K/V inside the handle; ctx_out (B, T_c, d) may be NULL.
+ * goal_path_lang: MDTB200_MODALITY_*.  */
+MDTB200_API int mdtb200_encode(MdtHandle* h, const float* goal, const float* state, int modality, int B,
+                   float* ctx_out, void* stream);
+
+/* forward_dec_only with an externally supplied context (mdtv_transformer.py:224-236):
+ * loads ctx (B, T_c, d) into the handle and recomputes the cross-attention K/V. */
+MDTB200_API int mdtb200_set_context(MdtHandle* h, const float* ctx, int B, void* stream);
+
+/* One score-network evaluation on the cached context.
+ *   precondition != 0: GCDenoiser.forward (score_wrappers.py:65-80):
+ *        out = inner(x * c_in(sigma), sigma) * c_out(sigma) + x * c_skip(sigma)
+ *   precondition == 0: raw MDTVTransformer.forward_dec_only(ctx, x, sigma).
+ * x, out: (B, T_a, action_dim); sigma: (B,) per-sample noise levels (device). */
+MDTB200_API int mdtb200_denoise(MdtHandle* h, const float* x, const float* sigma, int B, int precondition,
+                    float* out, void* stream);
+
+/* MDTVAgent.sample_loop for the fused samplers: encode once, then n_steps sampler iterations
+ * (each 1 score evaluation; Heun 2 except on the last step), all inside one CUDA graph that
+ * is cached per (B, n_steps, sampler, modality).
+ *   sigmas: (n_steps + 1,) DEVICE array, last entry 0 (get_sigmas_*: gc_sampling.py:26-88)
+ *   x_inout: (B, T_a, action_dim) device; holds x_T = randn * sigma_max on entry (drawn by the
+ *            caller, mdtv_agent.py:546) and the sampled actions x_0 on return. */
+MDTB200_API int mdtb200_sample(MdtHandle* h, int sampler, const float* sigmas, int n_steps,
+                   const float* goal, const float* state, int modality, int B,
+                   float* x_inout, void* stream);
+
+/* Same call on HOST buffers (what a non-torch host binds): copies goal/state/x_T/sigmas to the
+ * device, runs the graph, copies x_0 back and synchronises the stream before returning. */
+MDTB200_API int mdtb200_sample_host(MdtHandle* h, int sampler, const float* sigmas_host, int n_steps,
+                        const float* goal_host, const float* state_host, int modality, int B,
+                        float* x_inout_host, void* stream);
+
+/* introspection ---------------------------------------------------------------------------- */
+/* number of kernels this handle has launched (graph replays count their kernel nodes) */
+MDTB200_API int64_t mdtb200_launch_count(const MdtHandle* h);
+/* copy a named internal buffer (debug / parity tests): "ctx", "kv", "mod", "xh", "a", "qkv",
+ * "y", "h", "q" ... into dst (device, capacity in floats); returns #floats or <0 */
+MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* dst_dev, int64_t capacity, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDTB200_H_ */

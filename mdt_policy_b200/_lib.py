@@ -1,0 +1,97 @@
+"""ctypes binding of libmdtb200.so (include/mdtb200.h).  There is NO fallback: if the library cannot be
+loaded (or built with nvcc) every entry point of the package raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+ABI_VERSION = 1
+
+# enums of include/mdtb200.h
+VARIANT = {"mdtv": 0, "mdt": 1}
+PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+SAMPLER = {"ddim": 0, "euler": 1, "heun": 2, "dpmpp_2m": 3}
+MODALITY_VIS, MODALITY_LANG = 0, 1
+
+EXPORTS = [
+    "mdtb200_abi_version", "mdtb200_create", "mdtb200_destroy", "mdtb200_last_error",
+    "mdtb200_bind_weight", "mdtb200_commit_weights", "mdtb200_encode", "mdtb200_set_context",
+    "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
+    "mdtb200_debug_copy",
+]
+
+
+class MdtConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("variant", C.c_int32), ("embed_dim", C.c_int32), ("n_heads", C.c_int32),
+        ("n_enc_layers", C.c_int32), ("n_dec_layers", C.c_int32), ("action_dim", C.c_int32),
+        ("action_seq_len", C.c_int32), ("goal_dim", C.c_int32), ("obs_dim", C.c_int32),
+        ("n_state_tokens", C.c_int32), ("precision", C.c_int32), ("max_batch", C.c_int32),
+        ("sigma_data", C.c_float),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    vp, i32, i64, fp = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
+    lib.mdtb200_abi_version.restype = i32
+    lib.mdtb200_create.argtypes = [C.POINTER(MdtConfig), C.POINTER(vp)]
+    lib.mdtb200_create.restype = i32
+    lib.mdtb200_destroy.argtypes = [vp]
+    lib.mdtb200_destroy.restype = None
+    lib.mdtb200_last_error.argtypes = [vp]
+    lib.mdtb200_last_error.restype = C.c_char_p
+    lib.mdtb200_bind_weight.argtypes = [vp, C.c_char_p, fp, i64]
+    lib.mdtb200_bind_weight.restype = i32
+    lib.mdtb200_commit_weights.argtypes = [vp, vp]
+    lib.mdtb200_commit_weights.restype = i32
+    lib.mdtb200_encode.argtypes = [vp, fp, fp, i32, i32, fp, vp]
+    lib.mdtb200_encode.restype = i32
+    lib.mdtb200_set_context.argtypes = [vp, fp, i32, vp]
+    lib.mdtb200_set_context.restype = i32
+    lib.mdtb200_denoise.argtypes = [vp, fp, fp, i32, i32, fp, vp]
+    lib.mdtb200_denoise.restype = i32
+    lib.mdtb200_sample.argtypes = [vp, i32, fp, i32, fp, fp, i32, i32, fp, vp]
+    lib.mdtb200_sample.restype = i32
+    lib.mdtb200_sample_host.argtypes = [vp, i32, fp, i32, fp, fp, i32, i32, fp, vp]
+    lib.mdtb200_sample_host.restype = i32
+    lib.mdtb200_launch_count.argtypes = [vp]
+    lib.mdtb200_launch_count.restype = i64
+    lib.mdtb200_debug_copy.argtypes = [vp, C.c_char_p, fp, i64, vp]
+    lib.mdtb200_debug_copy.restype = i64
+    return lib
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Returns the loaded library; builds it with nvcc if the .so is absent.  Raises on failure."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    f"mdt_policy_b200: CUDA library {path} is missing and could not be built ({e}); "
+                    "there is no CPU fallback") from e
+        try:
+            lib = C.CDLL(path)
+        except OSError as e:
+            raise RuntimeError(f"mdt_policy_b200: cannot load {path}: {e}; there is no CPU fallback") from e
+        _declare(lib)
+        if lib.mdtb200_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"mdt_policy_b200: {path} has ABI {lib.mdtb200_abi_version()}, expected {ABI_VERSION}")
+        _lib = lib
+        return lib

@@ -1,0 +1,113 @@
+"""The hot-path methods of the reference agents (mdt/models/mdtv_agent.py:508-678, twin in mdt_agent.py),
+as a plain object around ``GCDenoiser`` -- no Lightning, no encoders.
+
+``DenoiseAgent`` is what ``MDTVAgent.denoise_actions / sample_loop / get_noise_schedule / diffusion_loss`` do
+once the perceptual and goal embeddings exist; the sampler knobs stay plain attributes that evaluation code
+overwrites by assignment (mdt/evaluation/mdt_evaluate.py:248-256).
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+
+from . import gc_sampling as gcs
+from . import utils
+
+
+class DenoiseAgent:
+    def __init__(self, model, device="cuda", act_window_size=10, action_dim=7, num_sampling_steps=10,
+                 sampler_type="ddim", noise_scheduler="exponential", sigma_data=0.5, sigma_min=0.001, sigma_max=80.0,
+                 sigma_sample_density_type="loglogistic"):
+        self.model = model
+        self.device = torch.device(device)
+        self.act_window_size = act_window_size
+        self.action_dim = action_dim
+        self.num_sampling_steps = num_sampling_steps
+        self.sampler_type = sampler_type
+        self.noise_scheduler = noise_scheduler
+        self.sigma_data, self.sigma_min, self.sigma_max = sigma_data, sigma_min, sigma_max
+        self.sigma_sample_density_type = sigma_sample_density_type
+
+    # mdtv_agent.py:660-678
+    def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):
+        if noise_schedule_type == 'karras':
+            return gcs.get_sigmas_karras(n_sampling_steps, self.sigma_min, self.sigma_max, 7, self.device)
+        if noise_schedule_type == 'exponential':
+            return gcs.get_sigmas_exponential(n_sampling_steps, self.sigma_min, self.sigma_max, self.device)
+        if noise_schedule_type == 'vp':
+            return gcs.get_sigmas_vp(n_sampling_steps, device=self.device)
+        if noise_schedule_type == 'linear':
+            return gcs.get_sigmas_linear(n_sampling_steps, self.sigma_min, self.sigma_max, device=self.device)
+        if noise_schedule_type == 'cosine_beta':
+            return gcs.cosine_beta_schedule(n_sampling_steps, device=self.device)
+        if noise_schedule_type == 've':
+            return gcs.get_sigmas_ve(n_sampling_steps, self.sigma_min, self.sigma_max, device=self.device)
+        if noise_schedule_type == 'iddpm':
+            return gcs.get_iddpm_sigmas(n_sampling_steps, self.sigma_min, self.sigma_max, device=self.device)
+        raise ValueError('Unknown noise schedule type')
+
+    # mdtv_agent.py:593-658 (the samplers this package restates; the others accept the same model callable)
+    def sample_loop(self, sigmas, x_t, state, goal, latent_plan, sampler_type, extra_args={}):
+        s_churn = extra_args.get('s_churn', 0)
+        s_min = extra_args.get('s_min', 0)
+        if sampler_type == 'ddim':
+            return gcs.sample_ddim(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'heun':
+            return gcs.sample_heun(self.model, state, x_t, goal, sigmas, s_churn=s_churn, s_tmin=s_min, disable=True)
+        if sampler_type == 'euler':
+            return gcs.sample_euler(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'euler_ancestral':
+            return gcs.sample_euler_ancestral(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'dpmpp_2m':
+            return gcs.sample_dpmpp_2m(self.model, state, x_t, goal, sigmas, disable=True)
+        raise ValueError('desired sampler type not found!')
+
+    # mdtv_agent.py:523-550
+    def denoise_actions(self, latent_plan, perceptual_emb, latent_goal, inference=False, extra_args={}, x_T=None):
+        sampling_steps = self.num_sampling_steps if inference else 10
+        self.model.eval()
+        ref = perceptual_emb['state_images'] if isinstance(perceptual_emb, dict) and 'state_images' in perceptual_emb else None
+        if ref is not None and latent_goal.dim() < ref.dim():
+            latent_goal = latent_goal.unsqueeze(1)
+        sigmas = self.get_noise_schedule(sampling_steps, self.noise_scheduler)
+        if x_T is None:
+            x_T = torch.randn((len(latent_goal), self.act_window_size, self.action_dim), device=self.device) * self.sigma_max
+        return self.sample_loop(sigmas, x_T, perceptual_emb, latent_goal, latent_plan, self.sampler_type, extra_args)
+
+    def denoise_actions_host(self, state_images_host, latent_goal_host, x_T_host, modality="lang", out_host=None):
+        """End-to-end call on HOST tensors (pinned or not): H2D copies of the inputs, the sampling graph, D2H copy
+        of the actions, one synchronisation.  This is the call bench.py's ``e2e`` number times."""
+        dev = self.device
+        state = {"state_images": state_images_host.to(dev, non_blocking=True), "modality": modality}
+        goal = latent_goal_host.to(dev, non_blocking=True)
+        x_T = x_T_host.to(dev, non_blocking=True)
+        actions = self.denoise_actions(None, state, goal, inference=True, x_T=x_T)
+        if out_host is None:
+            out_host = torch.empty(actions.shape, dtype=actions.dtype, pin_memory=True)
+        out_host.copy_(actions, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host
+
+    # mdtv_agent.py:552-591 (densities the shipped configs use)
+    def make_sample_density(self):
+        kind = self.sigma_sample_density_type
+        if kind == 'loglogistic':
+            return partial(utils.rand_log_logistic, loc=math.log(self.sigma_data), scale=0.5,
+                           min_value=self.sigma_min, max_value=self.sigma_max)
+        if kind == 'lognormal':
+            return partial(utils.rand_log_normal, loc=getattr(self, 'sigma_sample_density_mean', -1.2),
+                           scale=getattr(self, 'sigma_sample_density_std', 1.2))
+        if kind == 'loguniform':
+            return partial(utils.rand_log_uniform, min_value=self.sigma_min, max_value=self.sigma_max)
+        if kind == 'uniform':
+            return partial(utils.rand_uniform, min_value=self.sigma_min, max_value=self.sigma_max)
+        raise ValueError('Unknown sample density type')
+
+    # mdtv_agent.py:508-521 (forward value; see GCDenoiser.loss about the backward pass)
+    def diffusion_loss(self, perceptual_emb, latent_goal, actions):
+        sigmas = self.make_sample_density()(shape=(len(actions),), device=self.device).to(self.device)
+        noise = torch.randn_like(actions)
+        loss, _ = self.model.loss(perceptual_emb, actions, latent_goal, noise, sigmas)
+        return loss, sigmas, noise

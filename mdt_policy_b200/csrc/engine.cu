@@ -1,0 +1,791 @@
+// libmdtb200.so -- host orchestration and C ABI (include/mdtb200.h) of the MDT denoising hot path.
+//
+// Data layout in HBM (all fp32 unless noted; M = B*T_a token rows, Mc = B*T_c context rows):
+//   weights arena   packed copy of the reference state dict: per layer [Wq;Wk;Wv] (3d,d) fused,
+//                   all decoder cross-attention [Wk;Wv] stacked (L*2d, d), all AdaLN modulation
+//                   matrices stacked (L*6d, d); bf16 hi|lo split copies for the tensor-core path.
+//   xh  (M, d)      decoder residual stream          xe (Mc, d)  encoder residual stream
+//   a   (M, d)      LN(+modulate) output / GEMM A    qkv (M, 3d) y (M, d)   h (M, 4d)   q (M, d)
+//   ctx (Mc, d)     encoder output                   kv (Mc, L*2d) cross-attention K|V of every decoder layer
+//   mod (R, L*6d)   AdaLN shift/scale/gate table: R = n_steps rows when sampling (one sigma per step,
+//                   shared by the batch) or R = B rows for per-sample sigma (denoise / loss API)
+// One denoise step = a fixed kernel sequence (see decoder_eval); a full sampling call (encode + N steps)
+// is captured once into a CUDA graph per (B, N, sampler, modality) and replayed.
+#include "../../include/mdtb200.h"
+#include "kernels_simt.cuh"
+#include "gemm_tcgen05.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mdt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct EncLayerW {
+  const float *ln1_w, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_w, *ln2_b, *wfc, *bfc, *wproj, *bproj;
+  const __nv_bfloat16 *wqkv16, *wo16, *wfc16, *wproj16;
+};
+struct DecLayerW {
+  const float *ln1_w, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln3_w, *ln3_b, *wq, *bq, *wco, *bco, *ln2_w, *ln2_b, *wfc, *bfc, *wproj, *bproj;
+  const __nv_bfloat16 *wqkv16, *wo16, *wq16, *wco16, *wfc16, *wproj16;
+};
+struct Weights {
+  const float *goal0_w, *goal0_b, *goal2_w, *goal2_b;
+  const float *lang0_w, *lang0_b, *lang2_w, *lang2_b;
+  const float *tok_w, *tok_b, *incam_w, *incam_b, *pos_emb;
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  const float *enc_ln_w, *enc_ln_b, *dec_ln_w, *dec_ln_b;
+  const float *wkv_all, *bkv_all, *wmod_all, *bmod_all;
+  const __nv_bfloat16 *wkv_all16;
+  const float *sig1_w, *sig1_b, *sig3_w, *sig3_b;
+  const float *ae_w, *ae_b, *ap_w, *ap_b;
+};
+
+struct Bound { const float* ptr; int64_t numel; };
+
+struct GraphKey {
+  int B, n_steps, sampler, modality;
+  bool operator<(const GraphKey& o) const {
+    if (B != o.B) return B < o.B;
+    if (n_steps != o.n_steps) return n_steps < o.n_steps;
+    if (sampler != o.sampler) return sampler < o.sampler;
+    return modality < o.modality;
+  }
+};
+struct GraphEntry { cudaGraphExec_t exec; int64_t kernels; };
+
+}  // namespace
+
+struct MdtHandle {
+  MdtConfig cfg;
+  int device = 0;
+  int d = 0, H = 0, hd = 0, T = 0, Tc = 0, Ts = 0, A = 0, Le = 0, Ld = 0;
+  std::string err;
+  std::map<std::string, Bound> bound;
+  bool committed = false;
+  int ctx_B = 0;                  // batch of the cached context (0 = none)
+
+  float* arena = nullptr; size_t arena_floats = 0; size_t arena_used = 0;
+  __nv_bfloat16* arena16 = nullptr; size_t arena16_elems = 0; size_t arena16_used = 0;
+  Weights w;
+
+  // workspace
+  float *in_goal = nullptr, *in_state = nullptr, *x = nullptr, *x2 = nullptr, *dbuf = nullptr, *sigmas = nullptr, *out = nullptr;
+  float *gh = nullptr, *xe = nullptr, *ctx = nullptr, *kv = nullptr, *xh = nullptr, *a = nullptr, *qkv = nullptr, *y = nullptr, *hbuf = nullptr, *q = nullptr;
+  float *pe = nullptr, *sh = nullptr, *cs = nullptr, *mod = nullptr;
+  __nv_bfloat16 *a16 = nullptr, *y16 = nullptr, *h16 = nullptr;   // split-bf16 operand copies (hi | lo)
+  int mod_rows = 0;
+
+  cudaStream_t cap_stream = nullptr;
+  std::map<GraphKey, GraphEntry> graphs;
+  int64_t launches = 0;
+  int64_t capture_count = 0;      // kernels launched while capturing
+  bool capturing = false;
+  std::vector<void*> allocs;
+  tc::TmaEncoder tma;
+};
+
+namespace {
+
+int fail(MdtHandle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                             \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess) return fail(h, MDTB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+inline void count_launch(MdtHandle* h) { if (h->capturing) h->capture_count++; else h->launches++; }
+
+inline int check_launch(MdtHandle* h, const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, MDTB200_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+
+struct Gemm {
+  const float* A = nullptr; int lda = 0;                 // fp32 A (SIMT path)
+  const __nv_bfloat16* A16 = nullptr; int lda16 = 0;     // split-bf16 A (hi | lo at +K) for the tensor-core path
+  const float* W = nullptr; const __nv_bfloat16* W16 = nullptr; const float* bias = nullptr;
+  float* C = nullptr; int ldc = 0;
+  __nv_bfloat16* C16 = nullptr; int ldc16 = 0; int lo_off = 0;
+  const float* R = nullptr; int ldr = 0;
+  const float* gate = nullptr; int gate_stride = 0; int rows_per_group = 1;
+  int M = 0, N = 0, K = 0; int epi = EPI_NONE;
+  int gi = 0, go = 0, goff = 0;
+};
+
+int launch_sgemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
+  if (p.K % SG_BK != 0 || p.N % 4 != 0 || p.lda % 4 != 0) return fail(h, MDTB200_EINVAL, "sgemm: unsupported shape M=%d N=%d K=%d", p.M, p.N, p.K);
+  GemmArgs g{};
+  g.A = p.A; g.lda = p.lda; g.W = p.W; g.bias = p.bias; g.C = p.C; g.ldc = p.ldc; g.R = p.R; g.ldr = p.ldr;
+  g.gate = p.gate; g.gate_stride = p.gate_stride; g.rows_per_group = p.rows_per_group;
+  g.M = p.M; g.N = p.N; g.K = p.K; g.gi = p.gi; g.go = p.go; g.goff = p.goff;
+  g.C16 = p.C16; g.ldc16 = p.ldc16; g.lo_off = p.lo_off;
+  dim3 grid((p.N + SG_BN - 1) / SG_BN, (p.M + SG_BM - 1) / SG_BM);
+  switch (p.epi) {
+    case EPI_NONE: sgemm_tn_kernel<EPI_NONE><<<grid, SG_THREADS, 0, st>>>(g); break;
+    case EPI_GELU: sgemm_tn_kernel<EPI_GELU><<<grid, SG_THREADS, 0, st>>>(g); break;
+    case EPI_MISH: sgemm_tn_kernel<EPI_MISH><<<grid, SG_THREADS, 0, st>>>(g); break;
+    case EPI_SILU: sgemm_tn_kernel<EPI_SILU><<<grid, SG_THREADS, 0, st>>>(g); break;
+    case EPI_RES: sgemm_tn_kernel<EPI_RES><<<grid, SG_THREADS, 0, st>>>(g); break;
+    case EPI_RES_GATE: sgemm_tn_kernel<EPI_RES_GATE><<<grid, SG_THREADS, 0, st>>>(g); break;
+    default: return fail(h, MDTB200_EINVAL, "sgemm: bad epilogue %d", p.epi);
+  }
+  count_launch(h);
+  return check_launch(h, "sgemm_tn_kernel");
+}
+
+// GEMM dispatcher: tensor cores when the handle's precision asks for them and the operand is available in
+// split-bf16 form, exact fp32 CUDA cores otherwise (tiny GEMMs of the sigma path always stay fp32).
+int gemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
+  if (h->cfg.precision != MDTB200_PREC_FP32 && p.A16 && p.W16 && p.gi == 0) {
+    tc::TcGemm t{};
+    t.A16 = p.A16; t.lda16 = p.lda16; t.W16 = p.W16; t.bias = p.bias;
+    t.C = p.C; t.ldc = p.ldc; t.C16 = p.C16; t.ldc16 = p.ldc16; t.lo_off = p.lo_off;
+    t.R = p.R; t.ldr = p.ldr; t.gate = p.gate; t.gate_stride = p.gate_stride; t.rows_per_group = p.rows_per_group;
+    t.M = p.M; t.N = p.N; t.K = p.K; t.epi = p.epi;
+    t.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1;
+    const char* e = tc::launch_tc_gemm(h->tma, t, st);
+    if (e) return fail(h, MDTB200_ECUDA, "tcgen05 gemm (M=%d N=%d K=%d): %s", p.M, p.N, p.K, e);
+    count_launch(h);
+    return check_launch(h, "tc_gemm_kernel");
+  }
+  if (!p.A) return fail(h, MDTB200_EINVAL, "gemm: no fp32 operand for the CUDA-core path");
+  return launch_sgemm(h, p, st);
+}
+
+int launch_ln(MdtHandle* h, const float* x, float* out, __nv_bfloat16* out16, const float* w, const float* b,
+              const float* shift, const float* scale, int mod_stride, int M, cudaStream_t st) {
+  LnArgs a{};
+  a.x = x; a.out = out; a.out16 = out16; a.ld16 = 2 * h->d; a.lo_off = h->d; a.w = w; a.b = b; a.shift = shift; a.scale = scale;
+  a.mod_stride = mod_stride; a.rows_per_group = h->T; a.M = M; a.d = h->d;
+  int blocks = (M * 32 + 255) / 256;
+  switch (h->d / 128) {
+    case 1: ln_mod_kernel<1><<<blocks, 256, 0, st>>>(a); break;
+    case 2: ln_mod_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    case 3: ln_mod_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+    case 4: ln_mod_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 6: ln_mod_kernel<6><<<blocks, 256, 0, st>>>(a); break;
+    case 8: ln_mod_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    default: return fail(h, MDTB200_EUNSUPPORTED, "embed_dim %d not supported by ln kernel", h->d);
+  }
+  count_launch(h);
+  return check_launch(h, "ln_mod_kernel");
+}
+
+int launch_attn(MdtHandle* h, const float* q, int ldq, const float* k, const float* v, int ldkv, float* y, __nv_bfloat16* y16,
+                int B, int Tq, int Tk, int causal, cudaStream_t st) {
+  AttnArgs a{};
+  a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = h->d; a.y16 = y16; a.ld16 = 2 * h->d; a.lo_off = h->d;
+  a.B = B; a.H = h->H; a.hd = h->hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
+  a.scale = 1.0f / sqrtf((float)h->hd);
+  int items = B * h->H;
+  attention_kernel<<<(items + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(a);
+  count_launch(h);
+  return check_launch(h, "attention_kernel");
+}
+
+int launch_head(MdtHandle* h, HeadArgs a, cudaStream_t st) {
+  int blocks = (a.M * 32 + 255) / 256;
+  switch (h->d / 128) {
+    case 1: head_kernel<1><<<blocks, 256, 0, st>>>(a); break;
+    case 2: head_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    case 3: head_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+    case 4: head_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 6: head_kernel<6><<<blocks, 256, 0, st>>>(a); break;
+    case 8: head_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    default: return fail(h, MDTB200_EUNSUPPORTED, "embed_dim %d not supported by head kernel", h->d);
+  }
+  count_launch(h);
+  return check_launch(h, "head_kernel");
+}
+
+#define TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+
+inline bool use_tc(const MdtHandle* h) { return h->cfg.precision != MDTB200_PREC_FP32; }
+
+// ------------------------------------------------------------------------------------------ network pieces
+
+// cross-attention K/V of every decoder layer from the context: kv[Mc, L*2d] = ctx . Wkv_all^T + b
+int compute_kv(MdtHandle* h, int B, cudaStream_t st) {
+  Gemm g;
+  g.A = h->ctx; g.lda = h->d; g.W = h->w.wkv_all; g.bias = h->w.bkv_all; g.C = h->kv; g.ldc = h->Ld * 2 * h->d;
+  g.M = B * h->Tc; g.N = h->Ld * 2 * h->d; g.K = h->d;
+  return gemm(h, g, st);
+}
+
+// forward_enc_only (mdtv_transformer.py:213-222; mdt_transformer.py:211-229 for the MDT variant)
+int encoder(MdtHandle* h, const float* goal, const float* state, int modality, int B, cudaStream_t st) {
+  const int d = h->d, Tc = h->Tc, Ts = h->Ts, Mc = B * Tc;
+  const Weights& w = h->w;
+  const bool lang = modality == MDTB200_MODALITY_LANG && w.lang0_w != nullptr;
+  {  // goal MLP: Linear(goal_dim, 2d) -> GELU -> Linear(2d, d), written to context token 0
+    Gemm g;
+    g.A = goal; g.lda = h->cfg.goal_dim; g.W = lang ? w.lang0_w : w.goal0_w; g.bias = lang ? w.lang0_b : w.goal0_b;
+    g.C = h->gh; g.ldc = 2 * d; g.M = B; g.N = 2 * d; g.K = h->cfg.goal_dim; g.epi = EPI_GELU;
+    TRY(gemm(h, g, st));
+    Gemm g2;
+    g2.A = h->gh; g2.lda = 2 * d; g2.W = lang ? w.lang2_w : w.goal2_w; g2.bias = lang ? w.lang2_b : w.goal2_b;
+    g2.C = h->xe; g2.ldc = d; g2.M = B; g2.N = d; g2.K = 2 * d; g2.gi = 1; g2.go = Tc; g2.goff = 0;
+    TRY(gemm(h, g2, st));
+  }
+  if (h->cfg.variant == MDTB200_VARIANT_MDTV) {  // tok_emb on the n_state_tokens Voltron tokens -> context tokens 1..
+    Gemm g;
+    g.A = state; g.lda = h->cfg.obs_dim; g.W = w.tok_w; g.bias = w.tok_b; g.C = h->xe; g.ldc = d;
+    g.M = B * Ts; g.N = d; g.K = h->cfg.obs_dim; g.gi = Ts; g.go = Tc; g.goff = 1;
+    TRY(gemm(h, g, st));
+  } else {  // MDT: token 1 = tok_emb(static), token 2 = incam_embed(gripper); then learned pos_emb
+    for (int t = 0; t < 2; ++t) {
+      Gemm g;
+      g.A = state + (size_t)t * h->cfg.obs_dim; g.lda = 2 * h->cfg.obs_dim; g.W = t == 0 ? w.tok_w : w.incam_w; g.bias = t == 0 ? w.tok_b : w.incam_b;
+      g.C = h->xe; g.ldc = d; g.M = B; g.N = d; g.K = h->cfg.obs_dim; g.gi = 1; g.go = Tc; g.goff = 1 + t;
+      TRY(gemm(h, g, st));
+    }
+    int n = Mc * d;
+    add_pos_emb_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->xe, w.pos_emb, B, Tc, d);
+    count_launch(h);
+    TRY(check_launch(h, "add_pos_emb_kernel"));
+  }
+  const bool tcp = use_tc(h);
+  for (int l = 0; l < h->Le; ++l) {  // Block.forward, transformer_blocks.py:209-214
+    const EncLayerW& L = w.enc[l];
+    TRY(launch_ln(h, h->xe, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln1_w, L.ln1_b, nullptr, nullptr, 0, Mc, st));
+    Gemm g;
+    g.A = h->a; g.lda = d; g.A16 = h->a16; g.lda16 = 2 * d; g.W = L.wqkv; g.W16 = L.wqkv16; g.bias = L.bqkv; g.C = h->qkv; g.ldc = 3 * d;
+    g.M = Mc; g.N = 3 * d; g.K = d;
+    TRY(gemm(h, g, st));
+    TRY(launch_attn(h, h->qkv, 3 * d, h->qkv + d, h->qkv + 2 * d, 3 * d, tcp ? nullptr : h->y, tcp ? h->y16 : nullptr, B, Tc, Tc, 0, st));
+    Gemm o;
+    o.A = h->y; o.lda = d; o.A16 = h->y16; o.lda16 = 2 * d; o.W = L.wo; o.W16 = L.wo16; o.bias = L.bo; o.C = h->xe; o.ldc = d; o.R = h->xe; o.ldr = d;
+    o.M = Mc; o.N = d; o.K = d; o.epi = EPI_RES;
+    TRY(gemm(h, o, st));
+    TRY(launch_ln(h, h->xe, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln2_w, L.ln2_b, nullptr, nullptr, 0, Mc, st));
+    Gemm f;
+    f.A = h->a; f.lda = d; f.A16 = h->a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
+    f.C = tcp ? nullptr : h->hbuf; f.ldc = 4 * d; f.C16 = tcp ? h->h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
+    f.M = Mc; f.N = 4 * d; f.K = d; f.epi = EPI_GELU;
+    TRY(gemm(h, f, st));
+    Gemm p;
+    p.A = h->hbuf; p.lda = 4 * d; p.A16 = h->h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = h->xe; p.ldc = d; p.R = h->xe; p.ldr = d;
+    p.M = Mc; p.N = d; p.K = 4 * d; p.epi = EPI_RES;
+    TRY(gemm(h, p, st));
+  }
+  TRY(launch_ln(h, h->xe, h->ctx, nullptr, w.enc_ln_w, w.enc_ln_b, nullptr, nullptr, 0, Mc, st));
+  TRY(compute_kv(h, B, st));
+  h->ctx_B = B;
+  return 0;
+}
+
+// AdaLN table: mod[r, :] for R sigma values (process_sigma_embeddings :238-244, sigma_emb :169-174,
+// AdaLNZero :245-260 of every decoder layer, stacked).
+int sigma_path(MdtHandle* h, const float* sigma, int R, cudaStream_t st) {
+  const int d = h->d;
+  int n = R * (d / 2);
+  sigma_posemb_kernel<<<(n + 127) / 128, 128, 0, st>>>(sigma, R, d, h->pe);
+  count_launch(h);
+  TRY(check_launch(h, "sigma_posemb_kernel"));
+  Gemm g1;
+  g1.A = h->pe; g1.lda = d; g1.W = h->w.sig1_w; g1.bias = h->w.sig1_b; g1.C = h->sh; g1.ldc = 2 * d; g1.M = R; g1.N = 2 * d; g1.K = d; g1.epi = EPI_MISH;
+  TRY(gemm(h, g1, st));
+  Gemm g2;   // epilogue applies the SiLU of AdaLNZero.modulation[0] directly: c itself is never needed
+  g2.A = h->sh; g2.lda = 2 * d; g2.W = h->w.sig3_w; g2.bias = h->w.sig3_b; g2.C = h->cs; g2.ldc = d; g2.M = R; g2.N = d; g2.K = 2 * d; g2.epi = EPI_SILU;
+  TRY(gemm(h, g2, st));
+  Gemm g3;
+  g3.A = h->cs; g3.lda = d; g3.W = h->w.wmod_all; g3.bias = h->w.bmod_all; g3.C = h->mod; g3.ldc = h->Ld * 6 * d; g3.M = R; g3.N = h->Ld * 6 * d; g3.K = d;
+  TRY(gemm(h, g3, st));
+  return 0;
+}
+
+// One score-network evaluation (forward_dec_only :224-236 + ConditionedBlock :292-309) on the cached context.
+//   x_in     actions the network sees (before c_in scaling)
+//   mod      AdaLN rows for this evaluation; mod_stride = 0 -> one row shared by the batch
+//   sigma/sigma_stride   per-sample sigma for the c_in scaling (stride 0 -> shared)
+int decoder_eval(MdtHandle* h, const float* x_in, const float* mod, int mod_stride, const float* sigma, int sigma_stride,
+                 int precondition, int B, HeadArgs head, cudaStream_t st) {
+  const int d = h->d, T = h->T, Tc = h->Tc, M = B * T;
+  const Weights& w = h->w;
+  const bool tcp = use_tc(h);
+  {
+    ActEmbArgs a{};
+    a.x = x_in; a.sigma = sigma; a.sigma_stride = sigma_stride; a.T = T; a.A = h->A; a.d = d; a.M = M;
+    a.W = w.ae_w; a.b = w.ae_b; a.xh = h->xh; a.sigma_data = h->cfg.sigma_data; a.precondition = precondition;
+    int n = M * d;
+    action_embed_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+    count_launch(h);
+    TRY(check_launch(h, "action_embed_kernel"));
+  }
+  const int kvld = h->Ld * 2 * d;
+  for (int l = 0; l < h->Ld; ++l) {
+    const DecLayerW& L = w.dec[l];
+    const float* ml = mod + (size_t)l * 6 * d;   // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
+    // x += gate_msa * SelfAttn_causal(shift_msa + LN1(x) * scale_msa)
+    TRY(launch_ln(h, h->xh, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln1_w, L.ln1_b, ml, ml + d, mod_stride, M, st));
+    Gemm g;
+    g.A = h->a; g.lda = d; g.A16 = h->a16; g.lda16 = 2 * d; g.W = L.wqkv; g.W16 = L.wqkv16; g.bias = L.bqkv; g.C = h->qkv; g.ldc = 3 * d; g.M = M; g.N = 3 * d; g.K = d;
+    TRY(gemm(h, g, st));
+    TRY(launch_attn(h, h->qkv, 3 * d, h->qkv + d, h->qkv + 2 * d, 3 * d, tcp ? nullptr : h->y, tcp ? h->y16 : nullptr, B, T, T, 1, st));
+    Gemm o;
+    o.A = h->y; o.lda = d; o.A16 = h->y16; o.lda16 = 2 * d; o.W = L.wo; o.W16 = L.wo16; o.bias = L.bo; o.C = h->xh; o.ldc = d; o.R = h->xh; o.ldr = d;
+    o.gate = ml + 2 * d; o.gate_stride = mod_stride; o.rows_per_group = T; o.M = M; o.N = d; o.K = d; o.epi = EPI_RES_GATE;
+    TRY(gemm(h, o, st));
+    // x += CrossAttn_causal-top-left(LN3(x), ctx)       (ln3 is nn.LayerNorm with bias)
+    TRY(launch_ln(h, h->xh, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln3_w, L.ln3_b, nullptr, nullptr, 0, M, st));
+    Gemm cq;
+    cq.A = h->a; cq.lda = d; cq.A16 = h->a16; cq.lda16 = 2 * d; cq.W = L.wq; cq.W16 = L.wq16; cq.bias = L.bq; cq.C = h->q; cq.ldc = d; cq.M = M; cq.N = d; cq.K = d;
+    TRY(gemm(h, cq, st));
+    TRY(launch_attn(h, h->q, d, h->kv + (size_t)l * 2 * d, h->kv + (size_t)l * 2 * d + d, kvld, tcp ? nullptr : h->y, tcp ? h->y16 : nullptr, B, T, Tc, 1, st));
+    Gemm co;
+    co.A = h->y; co.lda = d; co.A16 = h->y16; co.lda16 = 2 * d; co.W = L.wco; co.W16 = L.wco16; co.bias = L.bco; co.C = h->xh; co.ldc = d; co.R = h->xh; co.ldr = d;
+    co.M = M; co.N = d; co.K = d; co.epi = EPI_RES;
+    TRY(gemm(h, co, st));
+    // x += gate_mlp * MLP(shift_mlp + LN2(x) * scale_mlp)
+    TRY(launch_ln(h, h->xh, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln2_w, L.ln2_b, ml + 3 * d, ml + 4 * d, mod_stride, M, st));
+    Gemm f;
+    f.A = h->a; f.lda = d; f.A16 = h->a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
+    f.C = tcp ? nullptr : h->hbuf; f.ldc = 4 * d; f.C16 = tcp ? h->h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
+    f.M = M; f.N = 4 * d; f.K = d; f.epi = EPI_GELU;
+    TRY(gemm(h, f, st));
+    Gemm p;
+    p.A = h->hbuf; p.lda = 4 * d; p.A16 = h->h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = h->xh; p.ldc = d; p.R = h->xh; p.ldr = d;
+    p.gate = ml + 5 * d; p.gate_stride = mod_stride; p.rows_per_group = T; p.M = M; p.N = d; p.K = 4 * d; p.epi = EPI_RES_GATE;
+    TRY(gemm(h, p, st));
+  }
+  head.xh = h->xh; head.lnw = w.dec_ln_w; head.lnb = w.dec_ln_b; head.W = w.ap_w; head.bias = w.ap_b;
+  head.M = M; head.d = d; head.A = h->A; head.T = T; head.sigma_data = h->cfg.sigma_data;
+  return launch_head(h, head, st);
+}
+
+// the whole sampling call on the handle's static buffers (captured into a graph by mdtb200_sample)
+int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cudaStream_t st) {
+  TRY(encoder(h, h->in_goal, h->in_state, modality, B, st));
+  TRY(sigma_path(h, h->sigmas, n_steps, st));   // one AdaLN row per step: sigma is shared by the batch
+  const size_t mrow = (size_t)h->Ld * 6 * h->d;
+  for (int i = 0; i < n_steps; ++i) {
+    HeadArgs hd{};
+    hd.x_in = h->x; hd.x_state = h->x; hd.x_aux = h->x2; hd.dbuf = h->dbuf; hd.sigmas = h->sigmas; hd.step = i; hd.n_steps = n_steps;
+    switch (sampler) {
+      case MDTB200_SAMPLER_DDIM: hd.mode = HEAD_DDIM; break;
+      case MDTB200_SAMPLER_EULER: hd.mode = HEAD_EULER; break;
+      case MDTB200_SAMPLER_HEUN: hd.mode = HEAD_HEUN1; break;
+      case MDTB200_SAMPLER_DPMPP_2M: hd.mode = HEAD_DPMPP2M; break;
+      default: return fail(h, MDTB200_EINVAL, "unknown sampler %d", sampler);
+    }
+    TRY(decoder_eval(h, h->x, h->mod + i * mrow, 0, h->sigmas + i, 0, 1, B, hd, st));
+    if (sampler == MDTB200_SAMPLER_HEUN && i + 1 < n_steps) {   // 2nd-order correction; the last step (sigma_next = 0) is Euler
+      HeadArgs h2 = hd;
+      h2.mode = HEAD_HEUN2; h2.x_in = h->x2;
+      TRY(decoder_eval(h, h->x2, h->mod + (i + 1) * mrow, 0, h->sigmas + i + 1, 0, 1, B, h2, st));
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ weights
+
+const float* need(MdtHandle* h, const std::string& name, int64_t numel, bool optional, bool& ok) {
+  auto it = h->bound.find(name);
+  if (it == h->bound.end()) {
+    if (!optional) { ok = false; fail(h, MDTB200_ESTATE, "weight '%s' was not bound", name.c_str()); }
+    return nullptr;
+  }
+  if (it->second.numel != numel) {
+    ok = false;
+    fail(h, MDTB200_EINVAL, "weight '%s': expected %lld elements, got %lld", name.c_str(), (long long)numel, (long long)it->second.numel);
+    return nullptr;
+  }
+  return it->second.ptr;
+}
+
+// copies `numel` floats from a bound tensor into the arena, returns the arena pointer
+struct Packer {
+  MdtHandle* h; cudaStream_t st; bool ok = true; std::string p;
+  float* take(size_t n) {
+    if (h->arena_used + n > h->arena_floats) { ok = false; fail(h, MDTB200_ENOMEM, "weight arena overflow"); return nullptr; }
+    float* r = h->arena + h->arena_used;
+    h->arena_used += (n + 31) / 32 * 32;   // keep 128-byte alignment
+    return r;
+  }
+  const float* copy(const std::string& name, int64_t numel, bool optional = false) {
+    const float* src = need(h, p + name, numel, optional, ok);
+    if (!src || !ok) return nullptr;
+    float* dst = take((size_t)numel);
+    if (!dst) return nullptr;
+    if (cudaMemcpyAsync(dst, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { ok = false; fail(h, MDTB200_ECUDA, "memcpy of %s failed", name.c_str()); }
+    return dst;
+  }
+  // concatenation of several tensors (all required)
+  const float* concat(const std::vector<std::pair<std::string, int64_t>>& parts) {
+    size_t total = 0;
+    for (auto& q : parts) total += (size_t)q.second;
+    float* dst = take(total);
+    if (!dst) return nullptr;
+    size_t off = 0;
+    for (auto& q : parts) {
+      const float* src = need(h, p + q.first, q.second, false, ok);
+      if (!ok) return nullptr;
+      if (cudaMemcpyAsync(dst + off, src, (size_t)q.second * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { ok = false; fail(h, MDTB200_ECUDA, "memcpy of %s failed", q.first.c_str()); return nullptr; }
+      off += (size_t)q.second;
+    }
+    return dst;
+  }
+  // split-bf16 copy (rows, 2*cols) of an arena matrix
+  const __nv_bfloat16* split(const float* src, int64_t rows, int cols) {
+    if (!src || !ok || !h->arena16) return nullptr;
+    size_t n = (size_t)rows * cols * 2;
+    if (h->arena16_used + n > h->arena16_elems) { ok = false; fail(h, MDTB200_ENOMEM, "bf16 weight arena overflow"); return nullptr; }
+    __nv_bfloat16* dst = h->arena16 + h->arena16_used;
+    h->arena16_used += (n + 63) / 64 * 64;
+    int64_t total = rows * cols;
+    split_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, rows, cols);
+    return dst;
+  }
+};
+
+size_t arena_size(const MdtHandle* h) {
+  const size_t d = h->d, G = h->cfg.goal_dim, O = h->cfg.obs_dim, A = h->A;
+  size_t n = 0;
+  n += 2 * (2 * d * G + 2 * d + d * 2 * d + d);            // goal_emb + lang_emb
+  n += 2 * (d * O + d) + 64 * d;                           // tok_emb, incam_embed, pos_emb
+  n += h->Le * (12 * d * d + 3 * d + 8 * d + 64 * 12);      // encoder layers (+optional biases/padding)
+  n += h->Ld * (14 * d * d + 3 * d + d + 12 * d + 64 * 18); // decoder layers
+  n += h->Ld * (2 * d * d + 2 * d) + h->Ld * (6 * d * d + 6 * d);
+  n += 4 * d + 2 * d * d * 2 + 3 * d + A * d * 2 + d + A + 64 * 64;
+  return n + (1 << 16);
+}
+
+int pack_weights(MdtHandle* h, cudaStream_t st) {
+  const int64_t d = h->d, G = h->cfg.goal_dim, O = h->cfg.obs_dim, A = h->A;
+  h->arena_used = 0; h->arena16_used = 0;
+  Packer pk{h, st};
+  pk.p = "inner_model.";
+  Weights& w = h->w;
+  w = Weights{};
+  w.goal0_w = pk.copy("goal_emb.0.weight", 2 * d * G); w.goal0_b = pk.copy("goal_emb.0.bias", 2 * d);
+  w.goal2_w = pk.copy("goal_emb.2.weight", d * 2 * d); w.goal2_b = pk.copy("goal_emb.2.bias", d);
+  w.lang0_w = pk.copy("lang_emb.0.weight", 2 * d * G, true);
+  if (w.lang0_w) {
+    w.lang0_b = pk.copy("lang_emb.0.bias", 2 * d); w.lang2_w = pk.copy("lang_emb.2.weight", d * 2 * d); w.lang2_b = pk.copy("lang_emb.2.bias", d);
+  }
+  w.tok_w = pk.copy("tok_emb.weight", d * O); w.tok_b = pk.copy("tok_emb.bias", d);
+  if (h->cfg.variant == MDTB200_VARIANT_MDT) {
+    w.incam_w = pk.copy("incam_embed.weight", d * O); w.incam_b = pk.copy("incam_embed.bias", d);
+    // pos_emb (1, goal_seq_len + action_seq_len, d): rows 0 and 1 are used by the encoder
+    auto it = h->bound.find("inner_model.pos_emb");
+    if (it == h->bound.end() || it->second.numel < 2 * d) return fail(h, MDTB200_ESTATE, "weight 'inner_model.pos_emb' missing or too small");
+    float* dst = pk.take((size_t)2 * d);
+    if (dst) cudaMemcpyAsync(dst, it->second.ptr, (size_t)2 * d * 4, cudaMemcpyDeviceToDevice, st);
+    w.pos_emb = dst;
+  }
+  w.enc.resize(h->Le);
+  for (int l = 0; l < h->Le && pk.ok; ++l) {
+    EncLayerW& L = w.enc[l];
+    std::string b = "encoder.blocks." + std::to_string(l) + ".";
+    L.ln1_w = pk.copy(b + "ln_1.weight", d); L.ln1_b = pk.copy(b + "ln_1.bias", d, true);
+    L.wqkv = pk.concat({{b + "attn.query.weight", d * d}, {b + "attn.key.weight", d * d}, {b + "attn.value.weight", d * d}});
+    L.bqkv = pk.concat({{b + "attn.query.bias", d}, {b + "attn.key.bias", d}, {b + "attn.value.bias", d}});
+    L.wo = pk.copy(b + "attn.c_proj.weight", d * d); L.bo = pk.copy(b + "attn.c_proj.bias", d, true);
+    L.ln2_w = pk.copy(b + "ln_2.weight", d); L.ln2_b = pk.copy(b + "ln_2.bias", d, true);
+    L.wfc = pk.copy(b + "mlp.c_fc.weight", 4 * d * d); L.bfc = pk.copy(b + "mlp.c_fc.bias", 4 * d, true);
+    L.wproj = pk.copy(b + "mlp.c_proj.weight", 4 * d * d); L.bproj = pk.copy(b + "mlp.c_proj.bias", d, true);
+    L.wqkv16 = pk.split(L.wqkv, 3 * d, (int)d); L.wo16 = pk.split(L.wo, d, (int)d);
+    L.wfc16 = pk.split(L.wfc, 4 * d, (int)d); L.wproj16 = pk.split(L.wproj, d, (int)(4 * d));
+  }
+  w.enc_ln_w = pk.copy("encoder.ln.weight", d); w.enc_ln_b = pk.copy("encoder.ln.bias", d, true);
+  w.dec.resize(h->Ld);
+  std::vector<std::pair<std::string, int64_t>> kvw, kvb, modw, modb;
+  for (int l = 0; l < h->Ld && pk.ok; ++l) {
+    DecLayerW& L = w.dec[l];
+    std::string b = "decoder.blocks." + std::to_string(l) + ".";
+    L.ln1_w = pk.copy(b + "ln_1.weight", d); L.ln1_b = pk.copy(b + "ln_1.bias", d, true);
+    L.wqkv = pk.concat({{b + "attn.query.weight", d * d}, {b + "attn.key.weight", d * d}, {b + "attn.value.weight", d * d}});
+    L.bqkv = pk.concat({{b + "attn.query.bias", d}, {b + "attn.key.bias", d}, {b + "attn.value.bias", d}});
+    L.wo = pk.copy(b + "attn.c_proj.weight", d * d); L.bo = pk.copy(b + "attn.c_proj.bias", d, true);
+    L.ln3_w = pk.copy(b + "ln3.weight", d); L.ln3_b = pk.copy(b + "ln3.bias", d);
+    L.wq = pk.copy(b + "cross_att.query.weight", d * d); L.bq = pk.copy(b + "cross_att.query.bias", d);
+    L.wco = pk.copy(b + "cross_att.c_proj.weight", d * d); L.bco = pk.copy(b + "cross_att.c_proj.bias", d, true);
+    L.ln2_w = pk.copy(b + "ln_2.weight", d); L.ln2_b = pk.copy(b + "ln_2.bias", d, true);
+    L.wfc = pk.copy(b + "mlp.c_fc.weight", 4 * d * d); L.bfc = pk.copy(b + "mlp.c_fc.bias", 4 * d, true);
+    L.wproj = pk.copy(b + "mlp.c_proj.weight", 4 * d * d); L.bproj = pk.copy(b + "mlp.c_proj.bias", d, true);
+    L.wqkv16 = pk.split(L.wqkv, 3 * d, (int)d); L.wo16 = pk.split(L.wo, d, (int)d); L.wq16 = pk.split(L.wq, d, (int)d);
+    L.wco16 = pk.split(L.wco, d, (int)d); L.wfc16 = pk.split(L.wfc, 4 * d, (int)d); L.wproj16 = pk.split(L.wproj, d, (int)(4 * d));
+    kvw.push_back({b + "cross_att.key.weight", d * d}); kvw.push_back({b + "cross_att.value.weight", d * d});
+    kvb.push_back({b + "cross_att.key.bias", d}); kvb.push_back({b + "cross_att.value.bias", d});
+    modw.push_back({b + "adaLN_zero.modulation.1.weight", 6 * d * d}); modb.push_back({b + "adaLN_zero.modulation.1.bias", 6 * d});
+  }
+  if (pk.ok) {
+    w.wkv_all = pk.concat(kvw); w.bkv_all = pk.concat(kvb);
+    w.wmod_all = pk.concat(modw); w.bmod_all = pk.concat(modb);
+  }
+  w.dec_ln_w = pk.copy("decoder.ln.weight", d); w.dec_ln_b = pk.copy("decoder.ln.bias", d, true);
+  w.sig1_w = pk.copy("sigma_emb.1.weight", 2 * d * d); w.sig1_b = pk.copy("sigma_emb.1.bias", 2 * d);
+  w.sig3_w = pk.copy("sigma_emb.3.weight", d * 2 * d); w.sig3_b = pk.copy("sigma_emb.3.bias", d);
+  w.ae_w = pk.copy("action_emb.weight", d * A); w.ae_b = pk.copy("action_emb.bias", d);
+  w.ap_w = pk.copy("action_pred.weight", A * d); w.ap_b = pk.copy("action_pred.bias", A);
+  if (!pk.ok) return h->err.empty() ? fail(h, MDTB200_ESTATE, "weight packing failed") : MDTB200_ESTATE;
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int dev_alloc(MdtHandle* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return fail(h, MDTB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+int check_ready(MdtHandle* h, int B) {
+  if (!h) return MDTB200_EINVAL;
+  if (!h->committed) return fail(h, MDTB200_ESTATE, "weights not committed (call mdtb200_commit_weights)");
+  if (B < 1 || B > h->cfg.max_batch) return fail(h, MDTB200_EINVAL, "batch %d outside [1, max_batch=%d]", B, h->cfg.max_batch);
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (dev != h->device) return fail(h, MDTB200_ESTATE, "handle belongs to device %d but device %d is current", h->device, dev);
+  return 0;
+}
+
+constexpr int MAX_STEPS = 256;
+
+}  // namespace
+
+// =========================================================================================== C ABI
+
+extern "C" {
+
+MDTB200_API int mdtb200_abi_version(void) { return MDTB200_ABI_VERSION; }
+
+MDTB200_API const char* mdtb200_last_error(const MdtHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
+  if (!cfg || !out) return fail(nullptr, MDTB200_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MDTB200_ABI_VERSION) return fail(nullptr, MDTB200_EINVAL, "abi_version %d != %d", cfg->abi_version, MDTB200_ABI_VERSION);
+  const int d = cfg->embed_dim;
+  if (d < 128 || d % 128 != 0 || d > 1024 || d / 128 == 5 || d / 128 == 7) return fail(nullptr, MDTB200_EUNSUPPORTED, "embed_dim %d unsupported (128,256,384,512,768,1024)", d);
+  if (cfg->n_heads < 1 || d % cfg->n_heads != 0 || d / cfg->n_heads > ATT_MAXHD) return fail(nullptr, MDTB200_EUNSUPPORTED, "n_heads %d unsupported for d=%d (head_dim <= %d)", cfg->n_heads, d, ATT_MAXHD);
+  if (cfg->action_seq_len < 1 || cfg->action_seq_len > ATT_MAXT) return fail(nullptr, MDTB200_EUNSUPPORTED, "action_seq_len %d > %d", cfg->action_seq_len, ATT_MAXT);
+  if (cfg->n_state_tokens < 1 || 1 + cfg->n_state_tokens > ATT_MAXT) return fail(nullptr, MDTB200_EUNSUPPORTED, "n_state_tokens %d unsupported", cfg->n_state_tokens);
+  if (cfg->variant != MDTB200_VARIANT_MDTV && cfg->variant != MDTB200_VARIANT_MDT) return fail(nullptr, MDTB200_EINVAL, "unknown variant %d", cfg->variant);
+  if (cfg->variant == MDTB200_VARIANT_MDT && cfg->n_state_tokens != 2) return fail(nullptr, MDTB200_EINVAL, "MDT variant has exactly 2 state tokens");
+  if (cfg->goal_dim % 16 || cfg->obs_dim % 16) return fail(nullptr, MDTB200_EUNSUPPORTED, "goal_dim/obs_dim must be multiples of 16");
+  if (cfg->action_dim < 1 || cfg->action_dim > 64) return fail(nullptr, MDTB200_EINVAL, "action_dim %d", cfg->action_dim);
+  if (cfg->n_enc_layers < 0 || cfg->n_dec_layers < 1 || cfg->max_batch < 1) return fail(nullptr, MDTB200_EINVAL, "bad layer count / max_batch");
+  if (cfg->precision < MDTB200_PREC_FP32 || cfg->precision > MDTB200_PREC_BF16) return fail(nullptr, MDTB200_EINVAL, "unknown precision %d", cfg->precision);
+  if (!(cfg->sigma_data > 0.f)) return fail(nullptr, MDTB200_EINVAL, "sigma_data must be > 0");
+
+  MdtHandle* h = new (std::nothrow) MdtHandle();
+  if (!h) return fail(nullptr, MDTB200_ENOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->d = d; h->H = cfg->n_heads; h->hd = d / cfg->n_heads; h->T = cfg->action_seq_len; h->Ts = cfg->n_state_tokens; h->Tc = 1 + cfg->n_state_tokens;
+  h->A = cfg->action_dim; h->Le = cfg->n_enc_layers; h->Ld = cfg->n_dec_layers;
+  int rc = 0;
+  auto bail = [&](int code) { g_create_error = h->err; mdtb200_destroy(h); return code; };
+  if (cudaGetDevice(&h->device) != cudaSuccess) { fail(h, MDTB200_ECUDA, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return bail(MDTB200_ECUDA); }
+  if (cfg->precision != MDTB200_PREC_FP32) {
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, h->device);
+    if (prop.major != 10) { fail(h, MDTB200_EUNSUPPORTED, "tensor-core precision needs an sm_100 device (found sm_%d%d)", prop.major, prop.minor); return bail(MDTB200_EUNSUPPORTED); }
+    const char* e = h->tma.init();
+    if (e) { fail(h, MDTB200_ECUDA, "TMA descriptor encoder unavailable: %s", e); return bail(MDTB200_ECUDA); }
+    e = tc::configure_kernels();
+    if (e) { fail(h, MDTB200_ECUDA, "tcgen05 kernel configuration failed: %s", e); return bail(MDTB200_ECUDA); }
+  }
+  const size_t B = cfg->max_batch, M = B * h->T, Dd = d;
+  h->arena_floats = arena_size(h);
+  if ((rc = dev_alloc(h, &h->arena, h->arena_floats))) return bail(rc);
+  if (cfg->precision != MDTB200_PREC_FP32) {
+    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 14 * Dd * Dd) + (1 << 16);
+    if ((rc = dev_alloc(h, &h->arena16, h->arena16_elems))) return bail(rc);
+  }
+  h->mod_rows = (int)(B > (size_t)MAX_STEPS ? B : (size_t)MAX_STEPS);
+  const size_t R = h->mod_rows;
+  if ((rc = dev_alloc(h, &h->in_goal, B * cfg->goal_dim)) || (rc = dev_alloc(h, &h->in_state, B * h->Ts * cfg->obs_dim)) ||
+      (rc = dev_alloc(h, &h->x, M * h->A)) || (rc = dev_alloc(h, &h->x2, M * h->A)) || (rc = dev_alloc(h, &h->dbuf, M * h->A)) || (rc = dev_alloc(h, &h->out, M * h->A)) ||
+      (rc = dev_alloc(h, &h->sigmas, (size_t)MAX_STEPS + 8 + B)) ||
+      (rc = dev_alloc(h, &h->gh, B * 2 * Dd)) || (rc = dev_alloc(h, &h->xe, M * Dd)) || (rc = dev_alloc(h, &h->ctx, M * Dd)) ||
+      (rc = dev_alloc(h, &h->kv, B * h->Tc * h->Ld * 2 * Dd)) || (rc = dev_alloc(h, &h->xh, M * Dd)) || (rc = dev_alloc(h, &h->a, M * Dd)) ||
+      (rc = dev_alloc(h, &h->qkv, M * 3 * Dd)) || (rc = dev_alloc(h, &h->y, M * Dd)) || (rc = dev_alloc(h, &h->hbuf, M * 4 * Dd)) || (rc = dev_alloc(h, &h->q, M * Dd)) ||
+      (rc = dev_alloc(h, &h->pe, R * Dd)) || (rc = dev_alloc(h, &h->sh, R * 2 * Dd)) || (rc = dev_alloc(h, &h->cs, R * Dd)) || (rc = dev_alloc(h, &h->mod, R * h->Ld * 6 * Dd)))
+    return bail(rc);
+  if (cfg->precision != MDTB200_PREC_FP32) {
+    // row counts padded to the 128-row MMA tile so TMA boxes never leave the allocation
+    const size_t Mp = (M + 127) / 128 * 128;
+    if ((rc = dev_alloc(h, &h->a16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->y16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->h16, Mp * 8 * Dd))) return bail(rc);
+    cudaMemset(h->a16, 0, Mp * 2 * Dd * 2); cudaMemset(h->y16, 0, Mp * 2 * Dd * 2); cudaMemset(h->h16, 0, Mp * 8 * Dd * 2);
+  }
+  if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(h, MDTB200_ECUDA, "cudaStreamCreate failed"); return bail(MDTB200_ECUDA); }
+  *out = h;
+  return 0;
+}
+
+MDTB200_API void mdtb200_destroy(MdtHandle* h) {
+  if (!h) return;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+MDTB200_API int mdtb200_bind_weight(MdtHandle* h, const char* name, const float* dev_ptr, int64_t numel) {
+  if (!h) return MDTB200_EINVAL;
+  if (!name || !dev_ptr || numel <= 0) return fail(h, MDTB200_EINVAL, "bind_weight: bad argument");
+  h->bound[name] = Bound{dev_ptr, numel};
+  return 0;
+}
+
+MDTB200_API int mdtb200_commit_weights(MdtHandle* h, void* stream) {
+  if (!h) return MDTB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  h->committed = false;
+  h->ctx_B = 0;
+  // cached graphs reference arena addresses: drop them, the layout may change with the set of bound tensors
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+  int rc = pack_weights(h, st);
+  h->bound.clear();   // source pointers are not retained
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  h->committed = true;
+  return 0;
+}
+
+MDTB200_API int mdtb200_encode(MdtHandle* h, const float* goal, const float* state, int modality, int B, float* ctx_out, void* stream) {
+  TRY(check_ready(h, B));
+  if (!goal || !state) return fail(h, MDTB200_EINVAL, "encode: null input");
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(encoder(h, goal, state, modality, B, st));
+  if (ctx_out) CUDA_TRY(h, cudaMemcpyAsync(ctx_out, h->ctx, (size_t)B * h->Tc * h->d * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+MDTB200_API int mdtb200_set_context(MdtHandle* h, const float* ctx, int B, void* stream) {
+  TRY(check_ready(h, B));
+  if (!ctx) return fail(h, MDTB200_EINVAL, "set_context: null input");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h, cudaMemcpyAsync(h->ctx, ctx, (size_t)B * h->Tc * h->d * 4, cudaMemcpyDeviceToDevice, st));
+  TRY(compute_kv(h, B, st));
+  h->ctx_B = B;
+  return 0;
+}
+
+MDTB200_API int mdtb200_denoise(MdtHandle* h, const float* x, const float* sigma, int B, int precondition, float* out, void* stream) {
+  TRY(check_ready(h, B));
+  if (!x || !sigma || !out) return fail(h, MDTB200_EINVAL, "denoise: null argument");
+  if (h->ctx_B != B) return fail(h, MDTB200_ESTATE, "denoise: cached context is for batch %d, call has batch %d (encode first)", h->ctx_B, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(sigma_path(h, sigma, B, st));
+  HeadArgs hd{};
+  hd.mode = precondition ? HEAD_DENOISE : HEAD_RAW; hd.x_in = x; hd.out = out; hd.sigma = sigma; hd.sigma_stride = 1;
+  return decoder_eval(h, x, h->mod, h->Ld * 6 * h->d, sigma, 1, precondition, B, hd, st);
+}
+
+static int get_graph(MdtHandle* h, int sampler, int n_steps, int modality, int B, GraphEntry** out) {
+  GraphKey key{B, n_steps, sampler, modality};
+  auto it = h->graphs.find(key);
+  if (it != h->graphs.end()) { *out = &it->second; return 0; }
+  cudaGraph_t graph = nullptr;
+  CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  h->capturing = true; h->capture_count = 0;
+  int rc = sample_body(h, sampler, n_steps, modality, B, h->cap_stream);
+  h->capturing = false;
+  cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  GraphEntry ge{};
+  ge.kernels = h->capture_count;
+  e = cudaGraphInstantiate(&ge.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  auto ins = h->graphs.emplace(key, ge);
+  *out = &ins.first->second;
+  return 0;
+}
+
+static int check_sample_args(MdtHandle* h, int sampler, int n_steps, int B, const void* a, const void* b, const void* c, const void* d) {
+  TRY(check_ready(h, B));
+  if (!a || !b || !c || !d) return fail(h, MDTB200_EINVAL, "sample: null argument");
+  if (n_steps < 1 || n_steps > MAX_STEPS) return fail(h, MDTB200_EINVAL, "n_steps %d outside [1, %d]", n_steps, MAX_STEPS);
+  if (sampler < MDTB200_SAMPLER_DDIM || sampler > MDTB200_SAMPLER_DPMPP_2M) return fail(h, MDTB200_EINVAL, "unknown sampler %d", sampler);
+  return 0;
+}
+
+static int sample_impl(MdtHandle* h, int sampler, const float* sigmas, int n_steps, const float* goal, const float* state, int modality, int B,
+                       float* x_inout, cudaStream_t st, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
+  TRY(check_sample_args(h, sampler, n_steps, B, sigmas, goal, state, x_inout));
+  GraphEntry* ge = nullptr;
+  TRY(get_graph(h, sampler, n_steps, modality != 0, B, &ge));
+  const size_t xb = (size_t)B * h->T * h->A * 4;
+  CUDA_TRY(h, cudaMemcpyAsync(h->sigmas, sigmas, (size_t)(n_steps + 1) * 4, in_kind, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->in_goal, goal, (size_t)B * h->cfg.goal_dim * 4, in_kind, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->in_state, state, (size_t)B * h->Ts * h->cfg.obs_dim * 4, in_kind, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->x, x_inout, xb, in_kind, st));
+  CUDA_TRY(h, cudaGraphLaunch(ge->exec, st));
+  h->launches += ge->kernels;
+  h->ctx_B = B;
+  CUDA_TRY(h, cudaMemcpyAsync(x_inout, h->x, xb, out_kind, st));
+  return 0;
+}
+
+MDTB200_API int mdtb200_sample(MdtHandle* h, int sampler, const float* sigmas, int n_steps, const float* goal, const float* state, int modality, int B,
+                   float* x_inout, void* stream) {
+  if (!h) return MDTB200_EINVAL;
+  return sample_impl(h, sampler, sigmas, n_steps, goal, state, modality, B, x_inout, (cudaStream_t)stream, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+}
+
+MDTB200_API int mdtb200_sample_host(MdtHandle* h, int sampler, const float* sigmas_host, int n_steps, const float* goal_host, const float* state_host, int modality,
+                        int B, float* x_inout_host, void* stream) {
+  if (!h) return MDTB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(sample_impl(h, sampler, sigmas_host, n_steps, goal_host, state_host, modality, B, x_inout_host, st, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return 0;
+}
+
+MDTB200_API int64_t mdtb200_launch_count(const MdtHandle* h) { return h ? h->launches : 0; }
+
+MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* dst_dev, int64_t capacity, void* stream) {
+  if (!h || !name || !dst_dev) return MDTB200_EINVAL;
+  const size_t Bm = h->cfg.max_batch, M = Bm * h->T, d = h->d;
+  struct Ent { const char* n; const float* p; size_t len; };
+  const Ent tab[] = {
+      {"ctx", h->ctx, M * d}, {"kv", h->kv, Bm * h->Tc * h->Ld * 2 * d}, {"mod", h->mod, (size_t)h->mod_rows * h->Ld * 6 * d},
+      {"xh", h->xh, M * d}, {"xe", h->xe, M * d}, {"a", h->a, M * d}, {"qkv", h->qkv, M * 3 * d}, {"y", h->y, M * d},
+      {"h", h->hbuf, M * 4 * d}, {"q", h->q, M * d}, {"pe", h->pe, (size_t)h->mod_rows * d}, {"cs", h->cs, (size_t)h->mod_rows * d},
+      {"x", h->x, M * h->A},
+  };
+  for (const Ent& e : tab) {
+    if (strcmp(e.n, name) == 0) {
+      size_t n = e.len < (size_t)capacity ? e.len : (size_t)capacity;
+      if (cudaMemcpyAsync(dst_dev, e.p, n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return fail(h, MDTB200_ECUDA, "debug_copy failed");
+      return (int64_t)n;
+    }
+  }
+  return fail(h, MDTB200_EINVAL, "debug_copy: unknown buffer '%s'", name);
+}
+
+}  // extern "C"

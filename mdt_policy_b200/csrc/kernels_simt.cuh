@@ -1,0 +1,476 @@
+// CUDA-core (fp32) kernels of the MDT denoising path: LayerNorm(+AdaLN modulate), tiny-sequence
+// attention, sigma embedding, action embedding, output head fused with the EDM preconditioner and
+// the sampler update, and an exact-fp32 tiled GEMM with fused epilogues.
+//
+// Math follows SURVEY.md Appendix B; reference lines are cited per kernel.  No fast-math: the
+// sampler relies on IEEE inf arithmetic (log(0) = -inf on the last DDIM step).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace mdt {
+
+// ------------------------------------------------------------------------------------------
+// activations (exact variants, matching ATen)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float mish(float x) {
+  float sp = x > 20.0f ? x : log1pf(expf(x));   // softplus with ATen's threshold
+  return x * tanhf(sp);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// split an fp32 value into bf16 hi + bf16 lo (round-to-nearest both): x ~= hi + lo, |err| <= 2^-17 |x|
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact fp32 GEMM:  C[M,N] = epi( A[M,K] . W[N,K]^T + bias[N] )
+// 128x64x16 tiles, 256 threads, 8x4 micro-tile per thread, register-prefetched double buffering.
+enum Epi : int { EPI_NONE = 0, EPI_GELU = 1, EPI_MISH = 2, EPI_SILU = 3, EPI_RES = 4, EPI_RES_GATE = 5 };
+
+struct GemmArgs {
+  const float* A; int lda;
+  const float* W;            // (N, K) row-major == nn.Linear.weight
+  const float* bias;         // (N) or nullptr
+  float* C; int ldc;
+  const float* R; int ldr;   // residual for EPI_RES / EPI_RES_GATE (may alias C)
+  const float* gate;         // EPI_RES_GATE: gate[(m / rows_per_group) * gate_stride + n]
+  int gate_stride; int rows_per_group;
+  int M, N, K;
+  int gi, go, goff;          // output-row remap: row = (m / gi) * go + goff + m % gi   (gi == 0: identity)
+  // optional split-bf16 copy of the result for the tensor-core path (hi at [row, n], lo at [row, K' + n])
+  __nv_bfloat16* C16; int ldc16; int lo_off;
+};
+
+constexpr int SG_BM = 128, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+
+template <int EPI>
+__global__ void __launch_bounds__(SG_THREADS) sgemm_tn_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][SG_BK][SG_BM + 4];
+  __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+
+  // global->register staging: A tile 128x16 = 512 float4 (2 per thread), W tile 64x16 = 256 float4 (1 per thread)
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  float4 ra0, ra1, rb;
+  auto gload = [&](int k0) {
+    int r0 = m0 + lrow, r1 = m0 + 64 + lrow;
+    ra0 = r0 < g.M ? *reinterpret_cast<const float4*>(g.A + (size_t)r0 * g.lda + k0 + lk) : make_float4(0, 0, 0, 0);
+    ra1 = r1 < g.M ? *reinterpret_cast<const float4*>(g.A + (size_t)r1 * g.lda + k0 + lk) : make_float4(0, 0, 0, 0);
+    int rn = n0 + lrow;
+    rb = rn < g.N ? *reinterpret_cast<const float4*>(g.W + (size_t)rn * g.K + k0 + lk) : make_float4(0, 0, 0, 0);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][lk + 0][lrow] = ra0.x; As[buf][lk + 1][lrow] = ra0.y; As[buf][lk + 2][lrow] = ra0.z; As[buf][lk + 3][lrow] = ra0.w;
+    As[buf][lk + 0][64 + lrow] = ra1.x; As[buf][lk + 1][64 + lrow] = ra1.y; As[buf][lk + 2][64 + lrow] = ra1.z; As[buf][lk + 3][64 + lrow] = ra1.w;
+    Bs[buf][lk + 0][lrow] = rb.x; Bs[buf][lk + 1][lrow] = rb.y; Bs[buf][lk + 2][lrow] = rb.z; Bs[buf][lk + 3][lrow] = rb.w;
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nk = g.K / SG_BK;
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) gload((kb + 1) * SG_BK);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+  const int nb = n0 + tx * 4;
+  if (nb >= g.N) return;
+  float bj[4] = {0.f, 0.f, 0.f, 0.f};
+  if (g.bias) {
+    float4 bb = *reinterpret_cast<const float4*>(g.bias + nb);
+    bj[0] = bb.x; bj[1] = bb.y; bj[2] = bb.z; bj[3] = bb.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+    int row = g.gi ? (m / g.gi) * g.go + g.goff + m % g.gi : m;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = acc[i][j] + bj[j];
+      if (EPI == EPI_GELU) t = gelu_erf(t);
+      if (EPI == EPI_MISH) t = mish(t);
+      if (EPI == EPI_SILU) t = silu(t);
+      v[j] = t;
+    }
+    if (EPI == EPI_RES || EPI == EPI_RES_GATE) {
+      float4 r = *reinterpret_cast<const float4*>(g.R + (size_t)row * g.ldr + nb);
+      if (EPI == EPI_RES_GATE) {
+        float4 gt = *reinterpret_cast<const float4*>(g.gate + (size_t)(m / g.rows_per_group) * g.gate_stride + nb);
+        v[0] = r.x + gt.x * v[0]; v[1] = r.y + gt.y * v[1]; v[2] = r.z + gt.z * v[2]; v[3] = r.w + gt.w * v[3];
+      } else {
+        v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+      }
+    }
+    if (g.C) *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + nb) = make_float4(v[0], v[1], v[2], v[3]);
+    if (g.C16) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+      __nv_bfloat16* ph = g.C16 + (size_t)row * g.ldc16 + nb;
+      *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
+      *reinterpret_cast<uint2*>(ph + g.lo_off) = *reinterpret_cast<uint2*>(lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over d (eps 1e-5, transformer_blocks.py:29-38) optionally followed by the AdaLN
+// modulate  shift + LN(x) * scale  (transformer_blocks.py:262-263).  One warp per row.
+// shift/scale row = (m / rows_per_group) * mod_stride  (mod_stride = 0: one sigma for the batch).
+// Writes fp32 `out` and/or the split-bf16 operand copy `out16` ([row, 0..d) hi, [row, lo_off..) lo).
+struct LnArgs {
+  const float* x; float* out; __nv_bfloat16* out16; int ld16; int lo_off;
+  const float* w; const float* b;            // LN affine (b may be null)
+  const float* shift; const float* scale;    // may be null (plain LN)
+  int mod_stride; int rows_per_group;
+  int M, d;
+};
+
+template <int VPL>   // float4 vectors per lane: d = 128 * VPL
+__global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.M) return;
+  const float* xr = a.x + (size_t)warp * a.d;
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)a.d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)a.d + 1e-5f);
+  const size_t mrow = (size_t)(warp / a.rows_per_group) * a.mod_stride;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 w = *reinterpret_cast<const float4*>(a.w + c);
+    float o[4] = {(v[i].x - mean) * rstd * w.x, (v[i].y - mean) * rstd * w.y, (v[i].z - mean) * rstd * w.z, (v[i].w - mean) * rstd * w.w};
+    if (a.b) {
+      float4 bb = *reinterpret_cast<const float4*>(a.b + c);
+      o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+    }
+    if (a.shift) {
+      float4 sh = *reinterpret_cast<const float4*>(a.shift + mrow + c);
+      float4 sc = *reinterpret_cast<const float4*>(a.scale + mrow + c);
+      o[0] = sh.x + o[0] * sc.x; o[1] = sh.y + o[1] * sc.y; o[2] = sh.z + o[2] * sc.z; o[3] = sh.w + o[3] * sc.w;
+    }
+    if (a.out) *reinterpret_cast<float4*>(a.out + (size_t)warp * a.d + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.out16) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_bf16(o[j], hi[j], lo[j]);
+      __nv_bfloat16* ph = a.out16 + (size_t)warp * a.ld16 + c;
+      *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
+      *reinterpret_cast<uint2*>(ph + a.lo_off) = *reinterpret_cast<uint2*>(lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention for tiny sequences (Tq, Tk <= 16), one warp per (sample, head).
+// transformer_blocks.py:119-158: softmax(q k^T / sqrt(hd) + mask) v, mask[i][j] = (j <= i) when
+// causal -- top-left aligned also for the non-square cross-attention (Tq=10, Tk=4).
+// q rows: q + (b*Tq + i) * ldq + head*hd ; k/v rows: (b*Tk + j) * ldkv.
+struct AttnArgs {
+  const float* q; int ldq;
+  const float* k; const float* v; int ldkv;
+  float* y; int ldy;                       // fp32 out (may be null)
+  __nv_bfloat16* y16; int ld16; int lo_off;  // split-bf16 out (may be null)
+  int B, H, hd, Tq, Tk, causal;
+  float scale;
+};
+
+constexpr int ATT_WARPS = 2;   // 2 x (3 x 16 x 65 + 16 x 17) floats = 27 KB static smem
+constexpr int ATT_MAXT = 16, ATT_MAXHD = 64;
+
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(AttnArgs a) {
+  __shared__ float sq[ATT_WARPS][ATT_MAXT][ATT_MAXHD + 1];
+  __shared__ float sk[ATT_WARPS][ATT_MAXT][ATT_MAXHD + 1];
+  __shared__ float sv[ATT_WARPS][ATT_MAXT][ATT_MAXHD + 1];
+  __shared__ float sp[ATT_WARPS][ATT_MAXT][ATT_MAXT + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * ATT_WARPS + w;
+  if (item >= a.B * a.H) return;
+  const int b = item / a.H, h = item % a.H;
+  const int hd = a.hd, Tq = a.Tq, Tk = a.Tk;
+  for (int e = lane; e < Tq * hd; e += 32) {
+    int i = e / hd, c = e % hd;
+    sq[w][i][c] = a.q[(size_t)(b * Tq + i) * a.ldq + h * hd + c];
+  }
+  for (int e = lane; e < Tk * hd; e += 32) {
+    int j = e / hd, c = e % hd;
+    sk[w][j][c] = a.k[(size_t)(b * Tk + j) * a.ldkv + h * hd + c];
+    sv[w][j][c] = a.v[(size_t)(b * Tk + j) * a.ldkv + h * hd + c];
+  }
+  __syncwarp();
+  for (int e = lane; e < Tq * Tk; e += 32) {
+    int i = e / Tk, j = e % Tk;
+    float s = 0.f;
+    for (int c = 0; c < hd; ++c) s = fmaf(sq[w][i][c], sk[w][j][c], s);
+    sp[w][i][j] = (a.causal && j > i) ? -INFINITY : s * a.scale;
+  }
+  __syncwarp();
+  if (lane < Tq) {
+    float mx = -INFINITY;
+    for (int j = 0; j < Tk; ++j) mx = fmaxf(mx, sp[w][lane][j]);
+    float sum = 0.f;
+    for (int j = 0; j < Tk; ++j) { float e = expf(sp[w][lane][j] - mx); sp[w][lane][j] = e; sum += e; }
+    float inv = 1.0f / sum;
+    for (int j = 0; j < Tk; ++j) sp[w][lane][j] *= inv;
+  }
+  __syncwarp();
+  for (int e = lane; e < Tq * hd; e += 32) {
+    int i = e / hd, c = e % hd;
+    float o = 0.f;
+    for (int j = 0; j < Tk; ++j) o = fmaf(sp[w][i][j], sv[w][j][c], o);
+    size_t row = (size_t)(b * Tq + i);
+    if (a.y) a.y[row * a.ldy + h * hd + c] = o;
+    if (a.y16) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(o, hi, lo);
+      a.y16[row * a.ld16 + h * hd + c] = hi;
+      a.y16[row * a.ld16 + a.lo_off + h * hd + c] = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sinusoidal sigma embedding: pe[r, :] = [sin(e f_k), cos(e f_k)], e = log(sigma_r)/4,
+// f_k = exp(-k ln(10000)/(half-1))      (mdtv_transformer.py:13-25, :238-244)
+__global__ void sigma_posemb_kernel(const float* __restrict__ sigma, int R, int d, float* __restrict__ pe) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int half = d / 2;
+  if (idx >= R * half) return;
+  int r = idx / half, k = idx % half;
+  float e = logf(sigma[r]) / 4.0f;
+  float fstep = -(float)(9.210340371976184 / (double)(half - 1));   // -ln(10000)/(half-1), rounded once like torch
+  float f = expf((float)k * fstep);
+  float ang = e * f;
+  pe[(size_t)r * d + k] = sinf(ang);
+  pe[(size_t)r * d + half + k] = cosf(ang);
+}
+
+// ------------------------------------------------------------------------------------------
+// EDM scalings (score_wrappers.py:31-43)
+__device__ __forceinline__ void edm_scalings(float sigma, float sd, float& c_skip, float& c_out, float& c_in) {
+  float s2 = sigma * sigma + sd * sd;
+  c_skip = (sd * sd) / s2;
+  c_out = sigma * sd / sqrtf(s2);
+  c_in = 1.0f / sqrtf(s2);
+}
+
+// action embedding: xh[m, :] = W_ae (x[m, :] * c_in(sigma_b)) + b_ae   (score_wrappers.py:79, mdtv_transformer.py:226)
+// sigma index = (m / T) * sigma_stride (0 -> one sigma for the batch).  precondition == 0: c_in = 1.
+struct ActEmbArgs {
+  const float* x; const float* sigma; int sigma_stride; int T; int A; int d; int M;
+  const float* W; const float* b; float* xh; float sigma_data; int precondition;
+};
+__global__ void action_embed_kernel(ActEmbArgs a) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.M * a.d) return;
+  int m = idx / a.d, n = idx % a.d;
+  float c_in = 1.f;
+  if (a.precondition) {
+    float cs, co;
+    edm_scalings(a.sigma[(size_t)(m / a.T) * a.sigma_stride], a.sigma_data, cs, co, c_in);
+  }
+  float acc = 0.f;
+  for (int j = 0; j < a.A; ++j) acc = fmaf(a.W[n * a.A + j], a.x[(size_t)m * a.A + j] * c_in, acc);
+  a.xh[idx] = acc + a.b[n];
+}
+
+// ------------------------------------------------------------------------------------------
+// Output head: LN_dec -> action_pred (d -> A) -> EDM precondition -> sampler update, one warp per
+// token row.  Sampler formulas: gc_sampling.py:922-951 (ddim), :164-210 (euler), :256-311 (heun),
+// :699-733 (dpmpp_2m); scalar coefficients are recomputed per row from the device sigma table
+// with the same fp32 op sequence torch uses on 0-dim tensors.
+enum HeadMode : int {
+  HEAD_RAW = 0,        // out = action_pred(LN(xh))                  (forward_dec_only)
+  HEAD_DENOISE = 1,    // out = raw * c_out + x * c_skip             (GCDenoiser.forward)
+  HEAD_DDIM = 2,       // x <- (s'/s) x - expm1(-h) D
+  HEAD_EULER = 3,      // x <- x + (x - D)/s * (s' - s)
+  HEAD_HEUN1 = 4,      // d = (x - D)/s ; dbuf = d ; x2 = x + d dt   (x kept)
+  HEAD_HEUN2 = 5,      // d2 = (x2 - D2)/s' ; x <- x + (dbuf + d2)/2 dt
+  HEAD_DPMPP2M = 6     // multistep with old denoised in dbuf
+};
+struct HeadArgs {
+  const float* xh; const float* lnw; const float* lnb; const float* W; const float* bias;  // W (A, d)
+  const float* x_in;      // actions the network was evaluated on (x, or x2 for HEUN2)
+  float* x_state;         // sampler state x (updated in place for sampler modes)
+  float* x_aux;           // HEUN: x2 buffer
+  float* dbuf;            // HEUN: d ; DPMPP2M: old denoised
+  float* out;             // RAW / DENOISE output
+  const float* sigma; int sigma_stride;   // per-sample sigma (RAW/DENOISE); sampler modes use sigmas[step]
+  const float* sigmas; int step; int n_steps;
+  int M, d, A, T, mode; float sigma_data;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.M) return;
+  const float* xr = a.xh + (size_t)warp * a.d;
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)a.d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)a.d + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 w = *reinterpret_cast<const float4*>(a.lnw + c);
+    v[i].x = (v[i].x - mean) * rstd * w.x; v[i].y = (v[i].y - mean) * rstd * w.y;
+    v[i].z = (v[i].z - mean) * rstd * w.z; v[i].w = (v[i].w - mean) * rstd * w.w;
+    if (a.lnb) {
+      float4 bb = *reinterpret_cast<const float4*>(a.lnb + c);
+      v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+    }
+  }
+  // sampler scalars (uniform over the batch)
+  float sig, sig_next = 0.f;
+  if (a.mode <= HEAD_DENOISE) {
+    sig = a.sigma ? a.sigma[(size_t)(warp / a.T) * a.sigma_stride] : 1.f;
+  } else {
+    sig = a.sigmas[a.mode == HEAD_HEUN2 ? a.step + 1 : a.step];
+    sig_next = a.sigmas[a.step + 1];
+  }
+  float c_skip = 0.f, c_out = 1.f, c_in;
+  if (a.mode != HEAD_RAW) edm_scalings(sig, a.sigma_data, c_skip, c_out, c_in);
+
+  for (int j = 0; j < a.A; ++j) {
+    const float* wr = a.W + (size_t)j * a.d;
+    float p = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 w = *reinterpret_cast<const float4*>(wr + (i * 32 + lane) * 4);
+      p += (v[i].x * w.x + v[i].y * w.y) + (v[i].z * w.z + v[i].w * w.w);
+    }
+    p = warp_sum(p);
+    if (lane == 0) {
+      const size_t e = (size_t)warp * a.A + j;
+      float raw = p + a.bias[j];
+      if (a.mode == HEAD_RAW) { a.out[e] = raw; continue; }
+      float xin = a.x_in[e];
+      float D = raw * c_out + xin * c_skip;
+      switch (a.mode) {
+        case HEAD_DENOISE: a.out[e] = D; break;
+        case HEAD_DDIM: {
+          float t = -logf(sig), tn = -logf(sig_next), h = tn - t;
+          a.x_state[e] = (expf(-tn) / expf(-t)) * xin - expm1f(-h) * D;
+        } break;
+        case HEAD_EULER: {
+          float dd = (xin - D) / sig;
+          a.x_state[e] = xin + dd * (sig_next - sig);
+        } break;
+        case HEAD_HEUN1: {
+          float dd = (xin - D) / sig, dt = sig_next - sig;
+          if (sig_next == 0.f) { a.x_state[e] = xin + dd * dt; }
+          else { a.dbuf[e] = dd; a.x_aux[e] = xin + dd * dt; }
+        } break;
+        case HEAD_HEUN2: {   // sig = sigma_{i+1}; x_in = x2; x_state still holds x
+          float s0 = a.sigmas[a.step], dt = sig - s0;
+          float d2 = (xin - D) / sig;
+          float dp = (a.dbuf[e] + d2) / 2.0f;
+          a.x_state[e] = a.x_state[e] + dp * dt;
+        } break;
+        case HEAD_DPMPP2M: {
+          float t = -logf(sig), tn = -logf(sig_next), h = tn - t;
+          float ratio = expf(-tn) / expf(-t), em = expm1f(-h);
+          float den = D;
+          if (a.step > 0 && sig_next != 0.f) {
+            float h_last = t - (-logf(a.sigmas[a.step - 1]));
+            float r = h_last / h;
+            den = (1.0f + 1.0f / (2.0f * r)) * D - (1.0f / (2.0f * r)) * a.dbuf[e];
+          }
+          a.x_state[e] = ratio * xin - em * den;
+          a.dbuf[e] = D;
+        } break;
+        default: break;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MDT variant: add the learned positional embedding rows to the encoder input
+// (mdt_transformer.py:318-324): token 0 += pos[0], tokens 1.. += pos[goal_seq_len] (t = 1).
+__global__ void add_pos_emb_kernel(float* x, const float* pos, int B, int Tc, int d) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Tc * d) return;
+  int c = idx % d, t = (idx / d) % Tc;
+  x[idx] += pos[(t == 0 ? 0 : 1) * d + c];
+}
+
+// fp32 -> split bf16 [rows, 2*cols] (hi | lo) conversion of a weight matrix (done once at commit)
+__global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int64_t rows, int cols) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols; int c = (int)(idx % cols);
+  __nv_bfloat16 hi, lo;
+  split_bf16(w[idx], hi, lo);
+  o[r * 2 * cols + c] = hi;
+  o[r * 2 * cols + cols + c] = lo;
+}
+
+}  // namespace mdt

@@ -1,0 +1,234 @@
+"""Noise schedules and samplers with the call contract of mdt/models/edm_diffusion/gc_sampling.py.
+
+``sample_ddim / sample_euler / sample_heun / sample_dpmpp_2m`` keep the reference signature
+``(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, ...)``.
+When ``model`` is this package's ``GCDenoiser`` and nothing in the call needs per-step host interaction
+(no callback, no scaler, no churn) the whole loop runs as ONE CUDA graph (``GCDenoiser.sample`` ->
+``mdtb200_sample``): encoder + cross-attention K/V once, the AdaLN table for all steps once, then N fused
+steps whose sampler update is folded into the output-head kernel.  Otherwise the generic loop below calls
+``model(...)`` once per evaluation exactly like the reference (each call = one ``mdtb200_denoise``).
+
+Samplers of the reference that are not restated here (lms, dpm_2, dpmpp_2s, ...) take any callable with the
+``model(state, action, goal, sigma)`` contract, so the reference's own functions run unchanged on top of this
+package's ``GCDenoiser``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import utils
+
+# --------------------------------------------------------------------------------------------------- schedules
+
+
+def append_zero(action):
+    return torch.cat([action, action.new_zeros([1])])
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7., device='cpu'):
+    """gc_sampling.py:26-32 -- Karras et al. (2022) rho-schedule."""
+    ramp = torch.linspace(0, 1, n)
+    lo, hi = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+    return append_zero((hi + ramp * (lo - hi)) ** rho).to(device)
+
+
+def get_sigmas_exponential(n, sigma_min, sigma_max, device='cpu'):
+    """gc_sampling.py:35-38 -- log-linear schedule (the default: conf/model/mdtv_agent.yaml noise_scheduler)."""
+    return append_zero(torch.linspace(math.log(sigma_max), math.log(sigma_min), n, device=device).exp())
+
+
+def get_sigmas_linear(n, sigma_min, sigma_max, device='cpu'):
+    """gc_sampling.py:41-44"""
+    return append_zero(torch.linspace(sigma_max, sigma_min, n, device=device))
+
+
+def cosine_beta_schedule(n, s=0.008, device='cpu'):
+    """gc_sampling.py:47-58"""
+    steps = n + 1
+    grid = np.linspace(0, steps, steps)
+    acp = np.cos(((grid / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    acp = acp / acp[0]
+    betas = np.clip(1 - (acp[1:] / acp[:-1]), a_min=0, a_max=0.999)
+    return append_zero(torch.tensor(np.flip(betas).copy(), device=device, dtype=torch.float32))
+
+
+def get_sigmas_ve(n, sigma_min=0.02, sigma_max=100, device='cpu'):
+    """gc_sampling.py:61-68"""
+    t = torch.linspace(0, n + 1, n, device=device)
+    return append_zero(torch.sqrt((sigma_max ** 2) * ((sigma_min ** 2 / sigma_max ** 2) ** (t / (n - 1)))))
+
+
+def get_sigmas_vp(n, beta_d=19.9, beta_min=0.1, eps_s=1e-3, device='cpu'):
+    """gc_sampling.py:84-88"""
+    t = torch.linspace(1, eps_s, n, device=device)
+    return append_zero(torch.sqrt(torch.exp(beta_d * t ** 2 / 2 + beta_min * t) - 1))
+
+
+def get_iddpm_sigmas(n, sigma_min=0.02, sigma_max=100, M=1000, j_0=0, C_1=0.001, C_2=0.008, device='cpu'):
+    """gc_sampling.py:71-81 (fp64 recursion, fp32 result)"""
+    idx = torch.arange(n, dtype=torch.float64, device=device)
+    u = torch.zeros(M + 1, dtype=torch.float64, device=device)
+
+    def alpha_bar(j):
+        return (0.5 * np.pi * j / M / (C_2 + 1)).sin() ** 2
+
+    for j in torch.arange(M, j_0, -1, device=device):
+        u[j - 1] = ((u[j] ** 2 + 1) / (alpha_bar(j - 1) / alpha_bar(j)).clip(min=C_1) - 1).sqrt()
+    kept = u[torch.logical_and(u >= sigma_min, u <= sigma_max)]
+    sig = kept[((len(kept) - 1) / (n - 1) * idx).round().to(torch.int64)]
+    return append_zero(sig).to(torch.float32)
+
+
+# --------------------------------------------------------------------------------------------------- helpers
+
+def to_d(action, sigma, denoised):
+    """Karras ODE derivative (gc_sampling.py:91-93)."""
+    return (action - denoised) / utils.append_dims(sigma, action.ndim)
+
+
+def get_ancestral_step(sigma_from, sigma_to, eta=1.):
+    """gc_sampling.py:102-109"""
+    if not eta:
+        return sigma_to, 0.
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+def _fused_ok(model, scaler, extra_args, callback) -> bool:
+    return (hasattr(model, "sample") and hasattr(model, "inner_model") and scaler is None and callback is None
+            and not extra_args)
+
+
+def _on_cuda(*tensors) -> bool:
+    return all(t.is_cuda for t in tensors if isinstance(t, torch.Tensor))
+
+
+# --------------------------------------------------------------------------------------------------- samplers
+
+@torch.no_grad()
+def sample_ddim(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.):
+    """DPM-Solver-1 / DDIM (gc_sampling.py:922-951): x <- (s'/s) x - expm1(-h) D, h = log s - log s'."""
+    extra_args = {} if extra_args is None else extra_args
+    if _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal):
+        return model.sample(state, action, goal, sigmas, sampler="ddim")
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in, **extra_args)
+        if callback is not None:
+            callback({'action': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        t, t_next = sigmas[i].log().neg(), sigmas[i + 1].log().neg()
+        h = t_next - t
+        action = (t_next.neg().exp() / t.neg().exp()) * action - (-h).expm1() * denoised
+    return action
+
+
+@torch.no_grad()
+def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                 s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
+    """Karras Algorithm 2 without the 2nd-order correction (gc_sampling.py:164-210)."""
+    extra_args = {} if extra_args is None else extra_args
+    if s_churn == 0 and _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal):
+        return model.sample(state, action, goal, sigmas, sampler="euler")
+    s_in = action.new_ones([action.shape[0]])
+    n = len(sigmas) - 1
+    for i in range(n):
+        gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + torch.randn_like(action) * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * s_in, **extra_args)
+        d = to_d(action, sigma_hat, denoised)
+        if callback is not None:
+            callback({'x': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigma_hat, 'denoised': denoised})
+        action = action + d * (sigmas[i + 1] - sigma_hat)
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+@torch.no_grad()
+def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
+    """Karras Algorithm 2 (Heun), gc_sampling.py:256-311: Euler predictor + trapezoidal corrector, plain Euler on
+    the last step (sigma_next == 0)."""
+    extra_args = {} if extra_args is None else extra_args
+    if (s_churn == 0 and _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal)
+            and float(sigmas[-1]) == 0.0 and bool((sigmas[:-1] > 0).all())):
+        return model.sample(state, action, goal, sigmas, sampler="heun")
+    s_in = action.new_ones([action.shape[0]])
+    n = len(sigmas) - 1
+    for i in range(n):
+        gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            action = action + torch.randn_like(action) * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = model(state, action, goal, sigma_hat * s_in, **extra_args)
+        d = to_d(action, sigma_hat, denoised)
+        if callback is not None:
+            callback({'x': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigma_hat, 'denoised': denoised})
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            action = action + d * dt
+        else:
+            action_2 = action + d * dt
+            denoised_2 = model(state, action_2, goal, sigmas[i + 1] * s_in, **extra_args)
+            d_2 = to_d(action_2, sigmas[i + 1], denoised_2)
+            action = action + (d + d_2) / 2 * dt
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+@torch.no_grad()
+def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                           disable=None, eta=1.):
+    """gc_sampling.py:213-253 (stochastic: always the generic loop, noise drawn by torch per step)."""
+    extra_args = {} if extra_args is None else extra_args
+    s_in = action.new_ones([action.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in, **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if callback is not None:
+            callback({'x': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        d = to_d(action, sigmas[i], denoised)
+        action = action + d * (sigma_down - sigmas[i])
+        if sigma_down > 0:
+            action = action + torch.randn_like(action) * sigma_up
+        if scaler is not None:
+            action = scaler.clip_output(action)
+    return action
+
+
+@torch.no_grad()
+def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
+    """DPM-Solver++(2M), gc_sampling.py:699-733."""
+    extra_args = {} if extra_args is None else extra_args
+    if _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal):
+        return model.sample(state, action, goal, sigmas, sampler="dpmpp_2m")
+    s_in = action.new_ones([action.shape[0]])
+    old_denoised = None
+    for i in range(len(sigmas) - 1):
+        denoised = model(state, action, goal, sigmas[i] * s_in, **extra_args)
+        if callback is not None:
+            callback({'action': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
+        t, t_next = sigmas[i].log().neg(), sigmas[i + 1].log().neg()
+        h = t_next - t
+        ratio = t_next.neg().exp() / t.neg().exp()
+        if old_denoised is None or sigmas[i + 1] == 0:
+            action = ratio * action - (-h).expm1() * denoised
+        else:
+            r = (t - sigmas[i - 1].log().neg()) / h
+            blend = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised
+            action = ratio * action - (-h).expm1() * blend
+        old_denoised = denoised
+    return action
+
+
+SAMPLERS = {
+    "ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "dpmpp_2m": sample_dpmpp_2m,
+    "euler_ancestral": sample_euler_ancestral,
+}
