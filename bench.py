@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- denoise-steps/sec of the MDT sampling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|fp32|bf16]
+
+A bench "step" is one pass of the hot path over one batch: a full 10-step DDIM sampling call
+(encode + 10 score-network evaluations) on B=256 synthetic environments per GPU, MDT-V config
+(conf/model/model/mdtv_transformer.yaml: d=384, 8 heads, 4 enc + 4 dec; --layers 6 gives the BASELINE-literal
+"6 layers" variant).  value = denoise-steps/s = n_gpus * K * 10 / t, with t = sum over the K timed calls of
+CUDA-event time (inputs already resident in HBM), max over ranks.  e2e = same through DenoiseAgent with pinned
+HOST buffers (H2D of state/goal/x_T and D2H of the actions inside the timed region).
+
+--impl reference: the reference's CPU implementation of the path (the oracle port: same ATen ops, encoder re-run
+on every evaluation exactly like the reference) on the box's host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoise-steps/sec (B=256, L=10, d=384, 10-step)"
+UNIT = "denoise-steps/s"
+N_STEPS = 10
+SIGMA_MIN, SIGMA_MAX = 0.001, 80.0
+# algorithmic FLOPs of the path (torch flop counter on the reference + attention math), MDT-V 4+4
+F_ENC, F_KV, F_SIGMA, F_CORE = 58_982_400, 9_437_184, 8_257_536, 166_118_400
+
+
+def alg_flops(B, n_steps, enc_layers, dec_layers):
+    """ALG(B, N) = B (F_enc + F_kv) + N (B F_core + F_sigma), scaled linearly in the layer counts."""
+    fe, fk = F_ENC * enc_layers / 4, F_KV * dec_layers / 4
+    fc = (F_CORE - 107_520) * dec_layers / 4 + 107_520
+    fs = 1_179_648 + 1_769_472 * dec_layers
+    return B * (fe + fk) + n_steps * (B * fc + fs)
+
+
+def inner_cfg(enc, dec, precision, max_batch):
+    return dict(
+        _target_="mdt_policy_b200.networks.MDTVTransformer", action_dim=7, obs_dim=384, goal_dim=512, proprio_dim=8,
+        goal_conditioned=True, embed_dim=384, n_dec_layers=dec, n_enc_layers=enc, n_obs_token=3, goal_seq_len=1,
+        obs_seq_len=1, action_seq_len=10, embed_pdrob=0, goal_drop=0, attn_pdrop=0.3, resid_pdrop=0.1, mlp_pdrop=0.05,
+        n_heads=8, device="cuda", linear_output=True, use_rot_embed=False, use_abs_pos_emb=True, bias=False,
+        use_ada_conditioning=True, use_noise_encoder=False, use_modality_encoder=True, use_mlp_goal=True,
+        precision=precision, max_batch=max_batch)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_tflops():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), "measured bf16 burst (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 1590.0, "fallback bf16 (B200_PROFILING.md)"
+
+
+def cpu_reference_run(enc, dec, B, steps, warmup, budget_s=150.0):
+    """The reference CPU arm: oracle port (same ATen kernels as the reference, encoder recomputed per evaluation),
+    all host threads.  Returns (denoise-steps/s scaled to B=256-batch evaluations, description dict)."""
+    from oracle import mdt_oracle as orc
+    from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs
+    from mdt_policy_b200 import GCDenoiser
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shapes = [(n, p.shape) for n, p in GCDenoiser(inner_cfg(enc, dec, "fp32", B), sigma_data=0.5).named_parameters()]
+    P = synthetic_state_dict(shapes, 12, "trained")     # parameter containers only: no product arithmetic on this arm
+    cfg = orc.OracleCfg(n_enc_layers=enc, n_dec_layers=dec)
+    inp = synthetic_inputs(B, seed=22)
+    sig = orc.get_sigmas_exponential(N_STEPS, SIGMA_MIN, SIGMA_MAX)
+
+    def call(n):
+        st = {"state_images": inp["state_images"][:n], "modality": "lang"}
+        t0 = time.perf_counter()
+        orc.sample(P, cfg, st, inp["x_T"][:n], inp["goal"][:n], sig, "ddim")
+        return time.perf_counter() - t0
+
+    t_full = call(B)                       # also serves as first warm-up
+    # bound the whole run: shrink the per-step sample (sub-batch of the same workload) if K full calls would not fit
+    sub = B
+    while sub > 8 and t_full * (sub / B) * (steps + warmup) > budget_s:
+        sub //= 2
+    for _ in range(max(0, warmup - 1)):
+        call(sub)
+    times = [call(sub) for _ in range(steps)]
+    total = sum(times)
+    value = steps * N_STEPS * (sub / B) / total      # full-batch(B)-equivalent score evaluations per second
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:  # noqa: BLE001
+        model = "unknown"
+    desc = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": model,
+            "sample": f"{steps} x 10-step DDIM calls on {sub} of {B} envs (fp32, torch {torch.__version__} CPU, {cores} threads); "
+                      f"best call {min(times) * 1e3:.0f} ms, mean {total / steps * 1e3:.0f} ms"}
+    return value, desc, total / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MDTB200_PRECISION", "bf16x3"))
+    ap.add_argument("--batch", type=int, default=256, help="environments per GPU")
+    ap.add_argument("--layers", type=int, default=4, help="4 = shipped MDT-V yaml (4 enc + 4 dec); 6 = BASELINE-literal 6+6")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    enc = dec = args.layers
+    B = args.batch
+    workload = (f"configs[1]: full {N_STEPS}-step EDM/DDIM sampling, batch={B}/GPU, MDT-V d=384 h=8 {enc}enc+{dec}dec, "
+                f"exponential sigmas {SIGMA_MAX}->{SIGMA_MIN}, synthetic CLIP/Voltron embeddings")
+    config = {"workload": workload, "batch_per_gpu": B, "sampling_steps": N_STEPS, "sampler": "ddim",
+              "enc_layers": enc, "dec_layers": dec, "parallelism": f"replica x{args.gpus} (envs sharded, no data-path collective)"}
+    warmup = max(args.warmup, 3)
+
+    from mdt_policy_b200 import dist as D
+    rank, local_rank, world = D.env_world()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        value, desc, ms = cpu_reference_run(enc, dec, B, args.steps, warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": desc,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: bench.py (impl=ours) measures the CUDA path only"}))
+        return 1
+    rank, local_rank, world = D.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    from mdt_policy_b200 import GCDenoiser, DenoiseAgent
+    from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs
+    model = GCDenoiser(inner_cfg(enc, dec, args.precision, B), sigma_data=0.5)
+    model.load_state_dict(synthetic_state_dict([(n, p.shape) for n, p in model.named_parameters()], 12, "trained"))
+    model = model.to(dev).eval()
+    agent = DenoiseAgent(model, device=dev, num_sampling_steps=N_STEPS, sampler_type="ddim", noise_scheduler="exponential",
+                         sigma_min=SIGMA_MIN, sigma_max=SIGMA_MAX)
+    inp = synthetic_inputs(B, seed=22 + rank)               # per-rank seed = base + rank (8 x 256 envs)
+    host = {k: inp[k].pin_memory() for k in ("state_images", "goal", "x_T")}
+    d_state = {"state_images": host["state_images"].to(dev), "modality": "lang"}
+    d_goal, d_xT = host["goal"].to(dev), host["x_T"].to(dev)
+    out_host = torch.empty(B, 10, 7, pin_memory=True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
+
+    def device_call():
+        return agent.denoise_actions(None, d_state, d_goal, inference=True, x_T=d_xT)
+
+    def host_call():
+        return agent.denoise_actions_host(host["state_images"], host["goal"], host["x_T"], "lang", out_host)
+
+    def timed(fn, k):
+        evs = []
+        for _ in range(k):
+            flush.zero_()                                   # evict L2 between timed iterations (untimed)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs) / 1e3
+
+    for _ in range(warmup):
+        device_call(); host_call()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+
+    D.barrier(); torch.cuda.synchronize()
+    l0 = model.inner_model.launch_count()
+    t_dev = timed(device_call, args.steps)
+    launches = model.inner_model.launch_count() - l0
+    D.barrier(); torch.cuda.synchronize()
+    t_e2e = timed(host_call, args.steps)
+    D.barrier(); torch.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+
+    agg = D.aggregate_throughput(args.steps * N_STEPS, t_dev, device=dev)      # the one collective: throughput counters
+    agg_e2e = D.aggregate_throughput(args.steps * N_STEPS, t_e2e, device=dev)
+    if rank != 0:
+        return 0
+
+    ms_per_step = agg["seconds"] / args.steps * 1e3
+    peak, peak_src = measured_peak_tflops()
+    flops = alg_flops(B, N_STEPS, enc, dec)
+    achieved = flops / (t_dev / args.steps) / 1e12
+    h2d = sum(host[k].numel() * 4 for k in host)
+    line = {
+        "metric": METRIC, "value": agg["throughput"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16x3": "bf16x3 (split-fp32 on tcgen05, fp32 accumulate)", "fp32": "f32", "bf16": "bf16"}[args.precision],
+        "data": "synthetic", "config": dict(config, l2="flushed between timed iterations (256 MiB write)", precision=args.precision),
+        "e2e": {"value": agg_e2e["throughput"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4,
+                "ms_per_step": agg_e2e["seconds"] / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "whole sampling graph (encode + 10 steps), algorithmic FLOPs ALG(B,N) of SURVEY 8d",
+                     "alg_gflop_per_launch": flops / 1e9, "peak_source": peak_src},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        _, desc, _ = cpu_reference_run(enc, dec, B, steps=5, warmup=2, budget_s=40.0)
+        line["cpu_baseline"] = desc
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

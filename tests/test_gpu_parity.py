@@ -1,0 +1,186 @@
+"""GPU parity tests proper: the CUDA path, called through the package's reference-facing API (-> ctypes -> C ABI),
+against (a) the committed golden vectors produced by the reference itself and (b) the CPU oracle on fresh seeded
+inputs.  Tolerances: 1e-4 max-abs on fp32 actions (BASELINE.json north_star); 2e-5 for the exact-fp32 CUDA-core
+mode; per-block context 1e-4 relative to O(1) activations."""
+import os
+
+import pytest
+import torch
+
+from oracle import mdt_oracle as orc
+from tests import helpers as H
+from mdt_policy_b200.synthetic import synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = os.environ.get("MDTB200_TEST_PRECISIONS", "fp32,bf16x3").split(",")
+TOL = {"fp32": 2e-5, "bf16x3": 1e-4}
+
+
+def _sigs():
+    return {"80": torch.full((4,), 80.0), "0p5": torch.full((4,), 0.5), "0p001": torch.full((4,), 0.001),
+            "mixed": torch.tensor([80.0, 3.1, 0.5, 0.001])}
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("profile", ["trained", "init"])
+def test_config1_forward_vs_golden(precision, profile):
+    """BASELINE config 1: single denoise forward, B=4, 2+2 layers, sigma in {80, 0.5, 0.001, mixed}."""
+    meta, gold = H.load_golden(f"config1_{profile}")
+    model = H.build_product(H.mdtv_inner_cfg(2, 2, precision=precision), meta["weight_seed"], profile)
+    inp = {k: v.cuda() for k, v in synthetic_inputs(4, seed=meta["input_seed"]).items()}
+    tol = TOL[precision]
+    with torch.no_grad():
+        for modality in ("lang", "vis"):
+            state = {"state_images": inp["state_images"], "modality": modality}
+            for tag, sig in _sigs().items():
+                sig = sig.cuda()
+                x = inp["noise"] * sig[:, None, None]
+                out = model(state, x, inp["goal"], sig).cpu()
+                ref = gold[f"fwd_{modality}_{tag}"]
+                assert (out - ref).abs().max() < tol * max(1.0, float(ref.abs().max())), (modality, tag, float((out - ref).abs().max()))
+            ctx = model.forward_context_only(state, inp["noise"], inp["goal"], torch.ones(4).cuda()).cpu()
+            assert (ctx - gold[f"ctx_{modality}"]).abs().max() < tol * 5
+            assert model.inner_model.latent_encoder_emb is not None
+        state = {"state_images": inp["state_images"], "modality": "lang"}
+        sig = _sigs()["mixed"].cuda()
+        raw = model.inner_model(state, inp["noise"] * sig[:, None, None], inp["goal"], sig).cpu()
+        assert (raw - gold["raw_lang_mixed"]).abs().max() < tol * max(1.0, float(gold["raw_lang_mixed"].abs().max()))
+        loss, out = model.loss(state, inp["actions"], inp["goal"], inp["noise"], sig)
+        assert abs(float(loss) - float(gold["loss_lang_mixed"])) < 1e-3 * max(1.0, float(gold["loss_lang_mixed"]))
+        assert (out.cpu() - gold["loss_out_lang_mixed"]).abs().max() < tol * max(1.0, float(gold["loss_out_lang_mixed"].abs().max()))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("profile", ["trained", "init"])
+def test_config2_full_sampling_vs_golden(precision, profile):
+    """BASELINE config 2 at full size: 10-step DDIM, B=256, MDT-V 4+4, both sigma_min settings."""
+    meta, gold = H.load_golden(f"config2_{profile}")
+    from mdt_policy_b200 import gc_sampling as gcs
+    model = H.build_product(H.mdtv_inner_cfg(4, 4, precision=precision), meta["weight_seed"], profile)
+    inp = {k: v.cuda() for k, v in synthetic_inputs(256, seed=meta["input_seed"]).items()}
+    state = {"state_images": inp["state_images"], "modality": "lang"}
+    for smin in (0.001, 1.0):
+        sig = gcs.get_sigmas_exponential(10, smin, 80.0, "cuda")
+        out = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], sig, disable=True).cpu()
+        ref32, ref64 = gold[f"ddim_smin{smin}_f32"], gold[f"ddim_smin{smin}_f64"].float()
+        e32, e64 = float((out - ref32).abs().max()), float((out - ref64).abs().max())
+        noise = float((ref32 - ref64).abs().max())
+        print(f"[config2 {profile} {precision} smin={smin}] |gpu-ref32|={e32:.2e} |gpu-ref64|={e64:.2e} |ref32-ref64|={noise:.2e}")
+        assert e32 < 1e-4, e32
+    # the other fused samplers + a 5-step Karras schedule (first 32 samples)
+    n = 32
+    st = {"state_images": inp["state_images"][:n], "modality": "lang"}
+    sig = gcs.get_sigmas_exponential(10, 0.001, 80.0, "cuda")
+    for fn, key in ((gcs.sample_euler, "euler_b32"), (gcs.sample_heun, "heun_b32"), (gcs.sample_dpmpp_2m, "dpmpp_2m_b32")):
+        out = fn(model, st, inp["x_T"][:n], inp["goal"][:n], sig, disable=True).cpu()
+        assert (out - gold[key]).abs().max() < 1e-4, key
+    out = gcs.sample_ddim(model, st, inp["x_T"][:n], inp["goal"][:n], gcs.get_sigmas_karras(5, 0.001, 80.0, device="cuda"), disable=True).cpu()
+    assert (out - gold["ddim_karras5_b32"]).abs().max() < 1e-4
+    ctx = model.forward_context_only(st, inp["x_T"][:n], inp["goal"][:n], torch.ones(n).cuda()).cpu()
+    assert (ctx - gold["ctx_b32"]).abs().max() < 1e-4 * 5
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_generic_loop_equals_fused_graph(precision):
+    """A callback forces the per-step host loop (one mdtb200_denoise per evaluation, encoder re-run each step like
+    the reference); it must agree with the fused CUDA-graph path."""
+    from mdt_policy_b200 import gc_sampling as gcs
+    model = H.build_product(H.mdtv_inner_cfg(2, 2, precision=precision), 31, "trained")
+    inp = {k: v.cuda() for k, v in synthetic_inputs(16, seed=32).items()}
+    state = {"state_images": inp["state_images"], "modality": "vis"}
+    sig = gcs.get_sigmas_exponential(7, 0.01, 80.0, "cuda")
+    seen = []
+    for fn in (gcs.sample_ddim, gcs.sample_euler, gcs.sample_heun, gcs.sample_dpmpp_2m):
+        fused = fn(model, state, inp["x_T"], inp["goal"], sig, disable=True)
+        loop = fn(model, state, inp["x_T"], inp["goal"], sig, disable=True, callback=lambda d: seen.append(d["i"]))
+        assert (fused - loop).abs().max() < 2e-5, fn.__name__
+    assert len(seen) == 4 * 7
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_six_by_six_and_mdt_variant(precision):
+    from mdt_policy_b200 import gc_sampling as gcs
+    meta, gold = H.load_golden("config2_6x6_trained")
+    model = H.build_product(H.mdtv_inner_cfg(6, 6, precision=precision), meta["weight_seed"], "trained")
+    inp = {k: v.cuda() for k, v in synthetic_inputs(32, seed=meta["input_seed"]).items()}
+    state = {"state_images": inp["state_images"], "modality": "vis"}
+    out = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], gcs.get_sigmas_exponential(10, 0.001, 80.0, "cuda"), disable=True).cpu()
+    assert (out - gold["ddim"]).abs().max() < 1e-4
+
+    meta, gold = H.load_golden("mdt_trained")
+    model = H.build_product(H.mdt_inner_cfg(precision=precision), meta["weight_seed"], "trained")
+    inp = {k: v.cuda() for k, v in synthetic_inputs(8, seed=meta["input_seed"], n_state_tokens=2, obs_dim=512).items()}
+    state = {"static": inp["state_images"][:, :1], "gripper": inp["state_images"][:, 1:], "modality": "lang"}
+    sigv = torch.tensor([80.0, 20.0, 5.0, 1.0, 0.5, 0.1, 0.01, 0.001]).cuda()
+    x = inp["noise"] * sigv[:, None, None]
+    with torch.no_grad():
+        fwd = model(state, x, inp["goal"], sigv).cpu()
+        assert (fwd - gold["fwd"]).abs().max() < 1e-4 * max(1.0, float(gold["fwd"].abs().max()))
+        ctx = model.forward_context_only(state, x, inp["goal"], sigv).cpu()
+        assert (ctx - gold["ctx"]).abs().max() < 5e-4
+    out = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], gcs.get_sigmas_exponential(10, 0.001, 80.0, "cuda"), disable=True).cpu()
+    assert (out - gold["ddim"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("B", [1, 3, 13, 129, 257])
+def test_ragged_batches_vs_oracle(precision, B):
+    """Edge sizes: single env (what reference rollouts use), non-multiples of every tile size, growth past max_batch."""
+    model = H.build_product(H.mdtv_inner_cfg(1, 2, precision=precision, max_batch=64), 41, "trained")
+    P = H.oracle_params([(n, p.shape) for n, p in model.named_parameters()], 41, "trained")
+    cfg = orc.OracleCfg(n_enc_layers=1, n_dec_layers=2)
+    inp = synthetic_inputs(B, seed=42 + B)
+    sig = torch.exp(torch.linspace(4.0, -6.0, B))
+    x = inp["noise"] * sig[:, None, None]
+    state = {"state_images": inp["state_images"], "modality": "lang"}
+    with torch.no_grad():
+        want = orc.denoiser_forward(P, cfg, state, x, inp["goal"], sig)
+        got = model({"state_images": inp["state_images"].cuda(), "modality": "lang"}, x.cuda(), inp["goal"].cuda(), sig.cuda()).cpu()
+    assert (got - want).abs().max() < TOL[precision] * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_properties(precision):
+    """Size-independent properties at BASELINE's full size (B=256, 4+4): run-to-run determinism (bit-exact),
+    per-environment independence (permuting the batch permutes the result, bit-exact), forward_dec_only on the
+    returned context == forward, the last DDIM step returns the denoised sample itself, goal input shapes."""
+    from mdt_policy_b200 import gc_sampling as gcs
+    model = H.build_product(H.mdtv_inner_cfg(4, 4, precision=precision), 51, "trained")
+    inp = {k: v.cuda() for k, v in synthetic_inputs(256, seed=52).items()}
+    state = {"state_images": inp["state_images"], "modality": "lang"}
+    sig = gcs.get_sigmas_exponential(10, 0.001, 80.0, "cuda")
+    a = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], sig, disable=True)
+    b = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], sig, disable=True)
+    assert torch.equal(a, b)
+    assert torch.isfinite(a).all()
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(0)).cuda()
+    c = gcs.sample_ddim(model, {"state_images": inp["state_images"][perm], "modality": "lang"}, inp["x_T"][perm], inp["goal"][perm], sig, disable=True)
+    assert torch.equal(c, a[perm])
+    with torch.no_grad():
+        s1 = torch.full((256,), 0.7, device="cuda")
+        full = model.inner_model(state, inp["noise"], inp["goal"], s1)
+        ctx = model.inner_model.forward_enc_only(state, None, inp["goal"], None)
+        dec = model.inner_model.forward_dec_only(ctx, inp["noise"], s1)
+        assert torch.equal(full, dec)
+        # goal given as (B, G) instead of (B, 1, G)  (preprocess_goals, mdtv_transformer.py:246-248)
+        assert torch.equal(model.inner_model(state, inp["noise"], inp["goal"][:, 0], s1), full)
+        # one-step DDIM from sigma to 0 returns D(x, sigma)
+        one = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], torch.tensor([80.0, 0.0], device="cuda"), disable=True)
+        den = model(state, inp["x_T"], inp["goal"], torch.full((256,), 80.0, device="cuda"))
+        assert (one - den).abs().max() < 1e-6
+    assert model.inner_model.launch_count() > 0
+
+
+def test_weights_resync_after_update():
+    """EMA swap / optimizer step / load_state_dict change parameters in place: the engine must re-commit."""
+    model = H.build_product(H.mdtv_inner_cfg(1, 1, precision="fp32"), 61, "trained")
+    inp = {k: v.cuda() for k, v in synthetic_inputs(4, seed=62).items()}
+    state = {"state_images": inp["state_images"], "modality": "lang"}
+    sig = torch.full((4,), 1.5, device="cuda")
+    with torch.no_grad():
+        a = model(state, inp["noise"], inp["goal"], sig)
+        model.inner_model.action_pred.bias.add_(1.0)
+        b = model(state, inp["noise"], inp["goal"], sig)
+    c_out = model.get_scalings(sig)[1][0]
+    assert (b - a - c_out).abs().max() < 1e-5
