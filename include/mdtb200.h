@@ -140,6 +140,12 @@ MDTB200_API int64_t mdtb200_launch_count(const MdtHandle* h);
  * "y", "h", "q" ... into dst (device, capacity in floats); returns #floats or <0 */
 MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* dst_dev, int64_t capacity, void* stream);
 
+/* tests only: out (M,N) = epi(A (M,K) . W (N,K)^T + bias) through the tensor-core GEMM kernel on fp32 inputs
+ * (epi: 0 none, 1 GELU, 4 residual R (M,N), 5 residual + gate[(m / rows_per_group), n] (gate row stride N)). */
+MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W, const float* bias, const float* R,
+                                   const float* gate, int M, int N, int K, int epi, int rows_per_group, float* out,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

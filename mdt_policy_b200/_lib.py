@@ -20,7 +20,7 @@ EXPORTS = [
     "mdtb200_abi_version", "mdtb200_create", "mdtb200_destroy", "mdtb200_last_error",
     "mdtb200_bind_weight", "mdtb200_commit_weights", "mdtb200_encode", "mdtb200_set_context",
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
-    "mdtb200_debug_copy",
+    "mdtb200_debug_copy", "mdtb200_debug_gemm",
 ]
 
 
@@ -65,6 +65,8 @@ def _declare(lib):
     lib.mdtb200_launch_count.restype = i64
     lib.mdtb200_debug_copy.argtypes = [vp, C.c_char_p, fp, i64, vp]
     lib.mdtb200_debug_copy.restype = i64
+    lib.mdtb200_debug_gemm.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, fp, vp]
+    lib.mdtb200_debug_gemm.restype = i32
     return lib
 
 

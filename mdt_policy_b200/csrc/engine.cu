@@ -70,6 +70,7 @@ struct MdtHandle {
   int device = 0;
   int d = 0, H = 0, hd = 0, T = 0, Tc = 0, Ts = 0, A = 0, Le = 0, Ld = 0;
   std::string err;
+  int last_code = 0;
   std::map<std::string, Bound> bound;
   bool committed = false;
   int ctx_B = 0;                  // batch of the cached context (0 = none)
@@ -97,6 +98,7 @@ struct MdtHandle {
 namespace {
 
 int fail(MdtHandle* h, int code, const char* fmt, ...) {
+  if (h) h->last_code = code;
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -230,10 +232,11 @@ inline bool use_tc(const MdtHandle* h) { return h->cfg.precision != MDTB200_PREC
 // ------------------------------------------------------------------------------------------ network pieces
 
 // cross-attention K/V of every decoder layer from the context: kv[Mc, L*2d] = ctx . Wkv_all^T + b
-int compute_kv(MdtHandle* h, int B, cudaStream_t st) {
+int compute_kv(MdtHandle* h, int B, cudaStream_t st, bool ctx_split_valid = false) {
   Gemm g;
   g.A = h->ctx; g.lda = h->d; g.W = h->w.wkv_all; g.bias = h->w.bkv_all; g.C = h->kv; g.ldc = h->Ld * 2 * h->d;
   g.M = B * h->Tc; g.N = h->Ld * 2 * h->d; g.K = h->d;
+  if (ctx_split_valid) { g.A16 = h->a16; g.lda16 = 2 * h->d; g.W16 = h->w.wkv_all16; }
   return gemm(h, g, st);
 }
 
@@ -293,8 +296,8 @@ int encoder(MdtHandle* h, const float* goal, const float* state, int modality, i
     p.M = Mc; p.N = d; p.K = 4 * d; p.epi = EPI_RES;
     TRY(gemm(h, p, st));
   }
-  TRY(launch_ln(h, h->xe, h->ctx, nullptr, w.enc_ln_w, w.enc_ln_b, nullptr, nullptr, 0, Mc, st));
-  TRY(compute_kv(h, B, st));
+  TRY(launch_ln(h, h->xe, h->ctx, tcp ? h->a16 : nullptr, w.enc_ln_w, w.enc_ln_b, nullptr, nullptr, 0, Mc, st));
+  TRY(compute_kv(h, B, st, tcp));
   h->ctx_B = B;
   return 0;
 }
@@ -478,7 +481,7 @@ size_t arena_size(const MdtHandle* h) {
 
 int pack_weights(MdtHandle* h, cudaStream_t st) {
   const int64_t d = h->d, G = h->cfg.goal_dim, O = h->cfg.obs_dim, A = h->A;
-  h->arena_used = 0; h->arena16_used = 0;
+  h->arena_used = 0; h->arena16_used = 0; h->last_code = 0;
   Packer pk{h, st};
   pk.p = "inner_model.";
   Weights& w = h->w;
@@ -538,13 +541,14 @@ int pack_weights(MdtHandle* h, cudaStream_t st) {
   if (pk.ok) {
     w.wkv_all = pk.concat(kvw); w.bkv_all = pk.concat(kvb);
     w.wmod_all = pk.concat(modw); w.bmod_all = pk.concat(modb);
+    w.wkv_all16 = pk.split(w.wkv_all, (int64_t)h->Ld * 2 * d, (int)d);
   }
   w.dec_ln_w = pk.copy("decoder.ln.weight", d); w.dec_ln_b = pk.copy("decoder.ln.bias", d, true);
   w.sig1_w = pk.copy("sigma_emb.1.weight", 2 * d * d); w.sig1_b = pk.copy("sigma_emb.1.bias", 2 * d);
   w.sig3_w = pk.copy("sigma_emb.3.weight", d * 2 * d); w.sig3_b = pk.copy("sigma_emb.3.bias", d);
   w.ae_w = pk.copy("action_emb.weight", d * A); w.ae_b = pk.copy("action_emb.bias", d);
   w.ap_w = pk.copy("action_pred.weight", A * d); w.ap_b = pk.copy("action_pred.bias", A);
-  if (!pk.ok) return h->err.empty() ? fail(h, MDTB200_ESTATE, "weight packing failed") : MDTB200_ESTATE;
+  if (!pk.ok) return h->last_code ? h->last_code : MDTB200_ESTATE;
   CUDA_TRY(h, cudaGetLastError());
   return 0;
 }
@@ -619,7 +623,7 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   h->arena_floats = arena_size(h);
   if ((rc = dev_alloc(h, &h->arena, h->arena_floats))) return bail(rc);
   if (cfg->precision != MDTB200_PREC_FP32) {
-    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 14 * Dd * Dd) + (1 << 16);
+    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 16 * Dd * Dd) + (1 << 16);
     if ((rc = dev_alloc(h, &h->arena16, h->arena16_elems))) return bail(rc);
   }
   h->mod_rows = (int)(B > (size_t)MAX_STEPS ? B : (size_t)MAX_STEPS);
@@ -786,6 +790,38 @@ MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* ds
     }
   }
   return fail(h, MDTB200_EINVAL, "debug_copy: unknown buffer '%s'", name);
+}
+
+// Standalone tensor-core GEMM on fp32 inputs (tests only): splits A (M,K) and W (N,K) into bf16 hi|lo, runs the
+// tcgen05 kernel with the handle's precision and writes fp32 out (M,N).  Synchronous; allocates scratch.
+MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W, const float* bias, const float* R, const float* gate,
+                                   int M, int N, int K, int epi, int rows_per_group, float* out, void* stream) {
+  if (!h || !A || !W || !out) return MDTB200_EINVAL;
+  if (h->cfg.precision == MDTB200_PREC_FP32) return fail(h, MDTB200_ESTATE, "debug_gemm needs a tensor-core precision handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16 *a16 = nullptr, *w16 = nullptr, *c16 = nullptr;
+  const size_t Mp = (size_t)(M + 127) / 128 * 128;
+  CUDA_TRY(h, cudaMalloc(&a16, Mp * 2 * K * 2));
+  CUDA_TRY(h, cudaMalloc(&w16, (size_t)N * 2 * K * 2));
+  CUDA_TRY(h, cudaMalloc(&c16, Mp * 2 * N * 2));
+  cudaMemsetAsync(a16, 0, Mp * 2 * K * 2, st);
+  split_weights_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, a16, M, K);
+  split_weights_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(W, w16, N, K);
+  Gemm g;
+  g.A16 = a16; g.lda16 = 2 * K; g.W16 = w16; g.bias = bias; g.C = out; g.ldc = N; g.C16 = c16; g.ldc16 = 2 * N; g.lo_off = N;
+  g.R = R; g.ldr = N; g.gate = gate; g.gate_stride = N; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  g.M = M; g.N = N; g.K = K; g.epi = epi;
+  int rc = gemm(h, g, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e == cudaSuccess) {
+    // fold the split-bf16 copy back (hi + lo) into the second half of `out` is not possible (size); verify it here instead:
+    // out16[m,n] = hi + lo must reproduce out within 2^-16 relative -- checked by the caller through mdtb200_debug_copy-free path
+  }
+  h->tma.cache.clear();
+  cudaFree(a16); cudaFree(w16); cudaFree(c16);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "debug_gemm: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 }  // extern "C"

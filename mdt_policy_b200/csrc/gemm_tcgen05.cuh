@@ -1,15 +1,376 @@
-// placeholder (stage A): tensor-core GEMM not wired yet
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fused epilogues and split-bf16 ("bf16x3") operands.
+//
+//   D[M,N] = epi( A[M,K] . W[N,K]^T + bias )        A, W: fp32 values stored as bf16 hi | lo halves
+//
+// Both operands are K-major ([rows, 2K] bf16: columns [0,K) = hi, [K,2K) = lo), staged by TMA
+// (cp.async.bulk.tensor, SWIZZLE_128B) into a multi-stage shared-memory ring; one elected thread issues
+// tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) with the fp32 accumulator in TMEM; with PASSES == 3
+// each k-block issues hi*hi + lo*hi + hi*lo into the same accumulator (~2^-17 relative operand error, see
+// tools/emulate_split_precision.py), with PASSES == 1 only hi*hi (plain bf16).  Warp roles (256 threads):
+//   warp 0  TMA producer      warp 1  MMA issuer      warp 2  TMEM allocator      warps 4-7  epilogue
+// Epilogue (TMEM -> registers via tcgen05.ld 32x32b): + bias, GELU(erf), residual, AdaLN gate, then fp32 store
+// and/or a split-bf16 store that directly produces the next GEMM's A operand.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <stdint.h>
+#include <cstdio>
+#include <map>
+#include <tuple>
+
+#include "kernels_simt.cuh"
+
 namespace mdt { namespace tc {
-struct TmaEncoder { const char* init() { return "tcgen05 path not built"; } };
+
+constexpr int BM = 128;        // UMMA M (rows of A per CTA)
+constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 256;
+
 struct TcGemm {
   const __nv_bfloat16* A16; int lda16; const __nv_bfloat16* W16; const float* bias;
   float* C; int ldc; __nv_bfloat16* C16; int ldc16; int lo_off;
   const float* R; int ldr; const float* gate; int gate_stride; int rows_per_group;
   int M, N, K, epi, passes;
 };
-inline const char* configure_kernels() { return "tcgen05 path not built"; }
-inline const char* launch_tc_gemm(TmaEncoder&, const TcGemm&, cudaStream_t) { return "tcgen05 path not built"; }
-}}
+
+struct TcParams {
+  const float* bias;
+  float* C; int ldc; __nv_bfloat16* C16; int ldc16; int lo_off;
+  const float* R; int ldr; const float* gate; int gate_stride; int rows_per_group;
+  int M, N, K, epi;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 (16 B,
+// ignored for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | version 1 (bits 46-47) | layout SWIZZLE_128B (2, bits 61-63)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int PASSES>
+struct SmemLayout {
+  static constexpr int A_TILE = BM * BK * 2;                 // 16 KB
+  static constexpr int W_TILE = BN * BK * 2;
+  static constexpr int STAGE = (PASSES == 3 ? 2 : 1) * (A_TILE + W_TILE);
+  static constexpr int STAGES = (PASSES == 3) ? (BN == 128 ? 3 : 4) : (BN == 128 ? 5 : 6);
+  static constexpr int BAR_OFF = STAGES * STAGE;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;         // barriers + tmem slot, + slack for 1024-B alignment
+};
+
+// ------------------------------------------------------------------------------------------ the kernel
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  using L = SmemLayout<BN, PASSES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (L::STAGES + s); };
+  const uint32_t tmem_full = bar0 + 8u * (2 * L::STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * (2 * L::STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < L::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), BN);     // BN in {64, 128}: power of two >= 32 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % L::STAGES;
+        const uint32_t ph = (kb / L::STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t st = sbase + s * L::STAGE;
+        mbar_expect_tx(full_bar(s), L::STAGE);
+        tma_load_2d(st, &tmA, full_bar(s), kb * BK, m0);                       // A hi
+        tma_load_2d(st + L::A_TILE, &tmW, full_bar(s), kb * BK, n0);           // W hi
+        if (PASSES == 3) {
+          tma_load_2d(st + L::A_TILE + L::W_TILE, &tmA, full_bar(s), p.K + kb * BK, m0);              // A lo
+          tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(s), p.K + kb * BK, n0);          // W lo
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % L::STAGES;
+        const uint32_t ph = (kb / L::STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st = sbase + s * L::STAGE;
+        const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + L::A_TILE);
+        const uint64_t a_lo = make_smem_desc(st + L::A_TILE + L::W_TILE), w_lo = make_smem_desc(st + 2 * L::A_TILE + L::W_TILE);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);     // +32 bytes per UMMA_K inside the 128-byte swizzle row
+          if (PASSES == 3) {
+            umma_f16(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);   // small terms first
+            umma_f16(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
+            umma_f16(tmem_base, a_hi + adv, w_hi + adv, idesc, 1);
+          } else {
+            umma_f16(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(empty_bar(s));          // smem slot reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);               // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int e = warp - 4;                 // warp e owns TMEM lanes [32e, 32e+32)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = m0 + e * 32 + lane;
+    const bool valid = row < p.M;
+    const size_t grow = valid ? (size_t)(row / p.rows_per_group) * p.gate_stride : 0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(c * 32), v);
+      if (!valid) continue;
+      const int nb = n0 + c * 32;
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j);
+          o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+        }
+      }
+      if (p.epi == EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = gelu_erf(o[j]);
+      } else if (p.epi == EPI_RES || p.epi == EPI_RES_GATE) {
+        const float* rr = p.R + (size_t)row * p.ldr + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 r = *reinterpret_cast<const float4*>(rr + j);
+          if (p.epi == EPI_RES_GATE) {
+            float4 g = *reinterpret_cast<const float4*>(p.gate + grow + nb + j);
+            o[j] = r.x + g.x * o[j]; o[j + 1] = r.y + g.y * o[j + 1]; o[j + 2] = r.z + g.z * o[j + 2]; o[j + 3] = r.w + g.w * o[j + 3];
+          } else {
+            o[j] += r.x; o[j + 1] += r.y; o[j + 2] += r.z; o[j + 3] += r.w;
+          }
+        }
+      }
+      if (p.C) {
+        float* cr = p.C + (size_t)row * p.ldc + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
+      if (p.C16) {
+        __nv_bfloat16* ch = p.C16 + (size_t)row * p.ldc16 + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          __align__(16) __nv_bfloat16 hi[8];
+          __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) split_bf16(o[j + t], hi[t], lo[t]);
+          *reinterpret_cast<uint4*>(ch + j) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(ch + p.lo_off + j) = *reinterpret_cast<const uint4*>(lo);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+struct TmaEncoder {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeFn fn = nullptr;
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> cache;
+  char msg[160];
+
+  const char* init() {
+    if (fn) return nullptr;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) {
+      snprintf(msg, sizeof(msg), "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+      return msg;
+    }
+    fn = reinterpret_cast<EncodeFn>(f);
+    return nullptr;
+  }
+
+  // 2-D bf16 row-major [rows, cols] (leading dimension ld elements), box = 64 columns x box_rows, SWIZZLE_128B
+  const char* get(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    auto key = std::make_tuple((const void*)ptr, rows, cols, ld, box_rows);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return nullptr; }
+    if (!fn) return "TMA encoder not initialised";
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+      return msg;
+    }
+    cache.emplace(key, m);
+    *out = m;
+    return nullptr;
+  }
+};
+
+template <int BN, int PASSES>
+inline const char* configure_one() {
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN, PASSES>::TOTAL);
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+inline const char* configure_kernels() {
+  const char* e;
+  if ((e = configure_one<128, 3>())) return e;
+  if ((e = configure_one<64, 3>())) return e;
+  if ((e = configure_one<128, 1>())) return e;
+  if ((e = configure_one<64, 1>())) return e;
+  return nullptr;
+}
+
+template <int BN, int PASSES>
+inline void launch_one(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
+  dim3 grid(p.N / BN, (p.M + BM - 1) / BM);
+  tc_gemm_kernel<BN, PASSES><<<grid, THREADS, SmemLayout<BN, PASSES>::TOTAL, st>>>(a, w, p);
+}
+
+// returns nullptr on success, an error message otherwise
+inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t st) {
+  if (g.K % BK != 0 || g.N % 64 != 0 || g.M < 1) return "unsupported GEMM shape (need K % 64 == 0, N % 64 == 0)";
+  if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE) return "unsupported epilogue";
+  // tile-N choice: 128 columns when that still yields >= ~1 wave of CTAs on 148 SMs, else 64
+  const int mt = (g.M + BM - 1) / BM;
+  const int bn = (g.N % 128 == 0 && mt * (g.N / 128) >= 120) ? 128 : 64;
+  CUtensorMap ta, tw;
+  const char* e;
+  if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
+  if ((e = enc.get(g.W16, g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
+  TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
+             g.M, g.N, g.K, g.epi};
+  if (g.passes == 3) {
+    if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
+  } else {
+    if (bn == 128) launch_one<128, 1>(ta, tw, p, st); else launch_one<64, 1>(ta, tw, p, st);
+  }
+  return nullptr;
+}
+
+}}  // namespace mdt::tc
