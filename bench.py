@@ -120,12 +120,14 @@ def cpu_reference_run(enc, dec, B, steps, warmup, budget_s=150.0):
 
     # give the CPU its best configuration: intra-op thread count calibrated on this host (all hardware threads is
     # often NOT the fastest for these small GEMMs), then every timed call uses the winner
-    cands = sorted({c for c in (cores, cores // 2, cores // 4, 64, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 64, 32, 16, 8) if 1 <= c <= cores})
     calib = {}
-    for c in cands:
+    for c in cands:                        # ascending; stop once more threads clearly hurt (oversubscription blows up fast)
         torch.set_num_threads(c)
-        call(32)
+        call(8)
         calib[c] = min(call(32), call(32))
+        if calib[c] > 1.5 * min(calib.values()):
+            break
     cores = min(calib, key=calib.get)
     torch.set_num_threads(cores)
     t_full = call(B)                       # also serves as first warm-up

@@ -148,12 +148,12 @@ int launch_sgemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
   g.C16 = p.C16; g.ldc16 = p.ldc16; g.lo_off = p.lo_off;
   dim3 grid((p.N + SG_BN - 1) / SG_BN, (p.M + SG_BM - 1) / SG_BM);
   switch (p.epi) {
-    case EPI_NONE: sgemm_tn_kernel<EPI_NONE><<<grid, SG_THREADS, 0, st>>>(g); break;
-    case EPI_GELU: sgemm_tn_kernel<EPI_GELU><<<grid, SG_THREADS, 0, st>>>(g); break;
-    case EPI_MISH: sgemm_tn_kernel<EPI_MISH><<<grid, SG_THREADS, 0, st>>>(g); break;
-    case EPI_SILU: sgemm_tn_kernel<EPI_SILU><<<grid, SG_THREADS, 0, st>>>(g); break;
-    case EPI_RES: sgemm_tn_kernel<EPI_RES><<<grid, SG_THREADS, 0, st>>>(g); break;
-    case EPI_RES_GATE: sgemm_tn_kernel<EPI_RES_GATE><<<grid, SG_THREADS, 0, st>>>(g); break;
+    case EPI_NONE: launch_pdl(sgemm_tn_kernel<EPI_NONE>, grid, dim3(SG_THREADS), 0, st, g); break;
+    case EPI_GELU: launch_pdl(sgemm_tn_kernel<EPI_GELU>, grid, dim3(SG_THREADS), 0, st, g); break;
+    case EPI_MISH: launch_pdl(sgemm_tn_kernel<EPI_MISH>, grid, dim3(SG_THREADS), 0, st, g); break;
+    case EPI_SILU: launch_pdl(sgemm_tn_kernel<EPI_SILU>, grid, dim3(SG_THREADS), 0, st, g); break;
+    case EPI_RES: launch_pdl(sgemm_tn_kernel<EPI_RES>, grid, dim3(SG_THREADS), 0, st, g); break;
+    case EPI_RES_GATE: launch_pdl(sgemm_tn_kernel<EPI_RES_GATE>, grid, dim3(SG_THREADS), 0, st, g); break;
     default: return fail(h, MDTB200_EINVAL, "sgemm: bad epilogue %d", p.epi);
   }
   count_launch(h);
@@ -186,12 +186,12 @@ int launch_ln(MdtHandle* h, const float* x, float* out, __nv_bfloat16* out16, co
   a.mod_stride = mod_stride; a.rows_per_group = h->T; a.M = M; a.d = h->d;
   int blocks = (M * 32 + 255) / 256;
   switch (h->d / 128) {
-    case 1: ln_mod_kernel<1><<<blocks, 256, 0, st>>>(a); break;
-    case 2: ln_mod_kernel<2><<<blocks, 256, 0, st>>>(a); break;
-    case 3: ln_mod_kernel<3><<<blocks, 256, 0, st>>>(a); break;
-    case 4: ln_mod_kernel<4><<<blocks, 256, 0, st>>>(a); break;
-    case 6: ln_mod_kernel<6><<<blocks, 256, 0, st>>>(a); break;
-    case 8: ln_mod_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    case 1: launch_pdl(ln_mod_kernel<1>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 2: launch_pdl(ln_mod_kernel<2>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 3: launch_pdl(ln_mod_kernel<3>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 4: launch_pdl(ln_mod_kernel<4>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 6: launch_pdl(ln_mod_kernel<6>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 8: launch_pdl(ln_mod_kernel<8>, dim3(blocks), dim3(256), 0, st, a); break;
     default: return fail(h, MDTB200_EUNSUPPORTED, "embed_dim %d not supported by ln kernel", h->d);
   }
   count_launch(h);
@@ -204,8 +204,7 @@ int launch_attn(MdtHandle* h, const float* q, int ldq, const float* k, const flo
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = h->d; a.y16 = y16; a.ld16 = 2 * h->d; a.lo_off = h->d;
   a.B = B; a.H = h->H; a.hd = h->hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
   a.scale = 1.0f / sqrtf((float)h->hd);
-  int items = B * h->H;
-  attention_kernel<<<(items + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(a);
+  launch_pdl(attention_kernel, dim3(B), dim3(ATT_THREADS), attention_smem_bytes(h->d, h->H, Tq, Tk), st, a);
   count_launch(h);
   return check_launch(h, "attention_kernel");
 }
@@ -213,12 +212,12 @@ int launch_attn(MdtHandle* h, const float* q, int ldq, const float* k, const flo
 int launch_head(MdtHandle* h, HeadArgs a, cudaStream_t st) {
   int blocks = (a.M * 32 + 255) / 256;
   switch (h->d / 128) {
-    case 1: head_kernel<1><<<blocks, 256, 0, st>>>(a); break;
-    case 2: head_kernel<2><<<blocks, 256, 0, st>>>(a); break;
-    case 3: head_kernel<3><<<blocks, 256, 0, st>>>(a); break;
-    case 4: head_kernel<4><<<blocks, 256, 0, st>>>(a); break;
-    case 6: head_kernel<6><<<blocks, 256, 0, st>>>(a); break;
-    case 8: head_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    case 1: launch_pdl(head_kernel<1>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 2: launch_pdl(head_kernel<2>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 3: launch_pdl(head_kernel<3>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 4: launch_pdl(head_kernel<4>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 6: launch_pdl(head_kernel<6>, dim3(blocks), dim3(256), 0, st, a); break;
+    case 8: launch_pdl(head_kernel<8>, dim3(blocks), dim3(256), 0, st, a); break;
     default: return fail(h, MDTB200_EUNSUPPORTED, "embed_dim %d not supported by head kernel", h->d);
   }
   count_launch(h);
@@ -268,7 +267,7 @@ int encoder(MdtHandle* h, const float* goal, const float* state, int modality, i
       TRY(gemm(h, g, st));
     }
     int n = Mc * d;
-    add_pos_emb_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->xe, w.pos_emb, B, Tc, d);
+    launch_pdl(add_pos_emb_kernel, dim3((n + 255) / 256), dim3(256), 0, st, h->xe, w.pos_emb, B, Tc, d);
     count_launch(h);
     TRY(check_launch(h, "add_pos_emb_kernel"));
   }
@@ -307,7 +306,7 @@ int encoder(MdtHandle* h, const float* goal, const float* state, int modality, i
 int sigma_path(MdtHandle* h, const float* sigma, int R, cudaStream_t st) {
   const int d = h->d;
   int n = R * (d / 2);
-  sigma_posemb_kernel<<<(n + 127) / 128, 128, 0, st>>>(sigma, R, d, h->pe);
+  launch_pdl(sigma_posemb_kernel, dim3((n + 127) / 128), dim3(128), 0, st, sigma, R, d, h->pe);
   count_launch(h);
   TRY(check_launch(h, "sigma_posemb_kernel"));
   Gemm g1;
@@ -336,7 +335,7 @@ int decoder_eval(MdtHandle* h, const float* x_in, const float* mod, int mod_stri
     a.x = x_in; a.sigma = sigma; a.sigma_stride = sigma_stride; a.T = T; a.A = h->A; a.d = d; a.M = M;
     a.W = w.ae_w; a.b = w.ae_b; a.xh = h->xh; a.sigma_data = h->cfg.sigma_data; a.precondition = precondition;
     int n = M * d;
-    action_embed_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+    launch_pdl(action_embed_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a);
     count_launch(h);
     TRY(check_launch(h, "action_embed_kernel"));
   }
@@ -642,6 +641,12 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
     if ((rc = dev_alloc(h, &h->a16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->y16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->h16, Mp * 8 * Dd))) return bail(rc);
     cudaMemset(h->a16, 0, Mp * 2 * Dd * 2); cudaMemset(h->y16, 0, Mp * 2 * Dd * 2); cudaMemset(h->h16, 0, Mp * 8 * Dd * 2);
   }
+  {
+    size_t att = attention_smem_bytes(d, h->H, h->T, h->T);
+    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att) != cudaSuccess) {
+      fail(h, MDTB200_ECUDA, "attention kernel needs %zu bytes of shared memory", att); return bail(MDTB200_ECUDA);
+    }
+  }
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(h, MDTB200_ECUDA, "cudaStreamCreate failed"); return bail(MDTB200_ECUDA); }
   *out = h;
   return 0;
@@ -692,7 +697,14 @@ MDTB200_API int mdtb200_set_context(MdtHandle* h, const float* ctx, int B, void*
   if (!ctx) return fail(h, MDTB200_EINVAL, "set_context: null input");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(h, cudaMemcpyAsync(h->ctx, ctx, (size_t)B * h->Tc * h->d * 4, cudaMemcpyDeviceToDevice, st));
-  TRY(compute_kv(h, B, st));
+  const bool tcp = use_tc(h);
+  if (tcp) {   // same split-bf16 operand the encoder's final LayerNorm would have produced
+    int64_t n = (int64_t)B * h->Tc * h->d;
+    split_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->ctx, h->a16, (int64_t)B * h->Tc, h->d);
+    count_launch(h);
+    TRY(check_launch(h, "split_weights_kernel"));
+  }
+  TRY(compute_kv(h, B, st, tcp));
   h->ctx_B = B;
   return 0;
 }

@@ -172,6 +172,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();      // prologue above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -349,7 +350,7 @@ inline const char* configure_kernels() {
 template <int BN, int PASSES>
 inline void launch_one(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
   dim3 grid(p.N / BN, (p.M + BM - 1) / BM);
-  tc_gemm_kernel<BN, PASSES><<<grid, THREADS, SmemLayout<BN, PASSES>::TOTAL, st>>>(a, w, p);
+  launch_pdl(tc_gemm_kernel<BN, PASSES>, grid, dim3(THREADS), SmemLayout<BN, PASSES>::TOTAL, st, a, w, p);
 }
 
 // returns nullptr on success, an error message otherwise

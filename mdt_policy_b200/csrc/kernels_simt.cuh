@@ -9,8 +9,33 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace mdt {
+
+// Host: launch with the programmatic-stream-serialization attribute (PDL).  MDTB200_PDL=0 disables it.
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MDTB200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Programmatic dependent launch (PDL): every kernel first lets its dependents start launching (their prologue
+// overlaps our tail), then waits until all prerequisite grids have completed and flushed before touching memory.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // activations (exact variants, matching ATen)
@@ -63,6 +88,7 @@ template <int EPI>
 __global__ void __launch_bounds__(SG_THREADS) sgemm_tn_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[2][SG_BK][SG_BM + 4];
   __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + 4];
+  pdl_enter();
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
@@ -172,6 +198,7 @@ struct LnArgs {
 
 template <int VPL>   // float4 vectors per lane: d = 128 * VPL
 __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const float* xr = a.x + (size_t)warp * a.d;
@@ -231,56 +258,75 @@ struct AttnArgs {
   float scale;
 };
 
-constexpr int ATT_WARPS = 2;   // 2 x (3 x 16 x 65 + 16 x 17) floats = 27 KB static smem
+constexpr int ATT_THREADS = 256;
 constexpr int ATT_MAXT = 16, ATT_MAXHD = 64;
 
-__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(AttnArgs a) {
-  __shared__ float sq[ATT_WARPS][ATT_MAXT][ATT_MAXHD + 1];
-  __shared__ float sk[ATT_WARPS][ATT_MAXT][ATT_MAXHD + 1];
-  __shared__ float sv[ATT_WARPS][ATT_MAXT][ATT_MAXHD + 1];
-  __shared__ float sp[ATT_WARPS][ATT_MAXT][ATT_MAXT + 1];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * ATT_WARPS + w;
-  if (item >= a.B * a.H) return;
-  const int b = item / a.H, h = item % a.H;
-  const int hd = a.hd, Tq = a.Tq, Tk = a.Tk;
-  for (int e = lane; e < Tq * hd; e += 32) {
-    int i = e / hd, c = e % hd;
-    sq[w][i][c] = a.q[(size_t)(b * Tq + i) * a.ldq + h * hd + c];
+// One CTA per sample: q/k/v rows of all heads are staged in shared memory with coalesced float4 loads
+// (row stride d + 4 floats keeps the per-key float4 reads of the score phase on distinct banks), then
+//   phase 1: all H*Tq*Tk scores (one dot product of length hd per thread, causal entries = -inf)
+//   phase 2: row softmax (H*Tq rows)          phase 3: P.V for the Tq*d outputs, written coalesced.
+inline size_t attention_smem_bytes(int d, int H, int Tq, int Tk) {
+  return ((size_t)(Tq + 2 * Tk) * (d + 4) + (size_t)H * Tq * (Tk + 1)) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) float att_smem[];
+  pdl_enter();
+  const int D = a.H * a.hd, DP = D + 4, Tq = a.Tq, Tk = a.Tk, hd = a.hd;
+  float* sq = att_smem;
+  float* sk = sq + Tq * DP;
+  float* sv = sk + Tk * DP;
+  float* sp = sv + Tk * DP;            // [H][Tq][Tk+1]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int D4 = D / 4;
+  for (int e = tid; e < Tq * D4; e += ATT_THREADS) {
+    int r = e / D4, c = (e % D4) * 4;
+    *reinterpret_cast<float4*>(sq + r * DP + c) = *reinterpret_cast<const float4*>(a.q + (size_t)(b * Tq + r) * a.ldq + c);
   }
-  for (int e = lane; e < Tk * hd; e += 32) {
-    int j = e / hd, c = e % hd;
-    sk[w][j][c] = a.k[(size_t)(b * Tk + j) * a.ldkv + h * hd + c];
-    sv[w][j][c] = a.v[(size_t)(b * Tk + j) * a.ldkv + h * hd + c];
+  for (int e = tid; e < Tk * D4; e += ATT_THREADS) {
+    int r = e / D4, c = (e % D4) * 4;
+    *reinterpret_cast<float4*>(sk + r * DP + c) = *reinterpret_cast<const float4*>(a.k + (size_t)(b * Tk + r) * a.ldkv + c);
+    *reinterpret_cast<float4*>(sv + r * DP + c) = *reinterpret_cast<const float4*>(a.v + (size_t)(b * Tk + r) * a.ldkv + c);
   }
-  __syncwarp();
-  for (int e = lane; e < Tq * Tk; e += 32) {
-    int i = e / Tk, j = e % Tk;
-    float s = 0.f;
-    for (int c = 0; c < hd; ++c) s = fmaf(sq[w][i][c], sk[w][j][c], s);
-    sp[w][i][j] = (a.causal && j > i) ? -INFINITY : s * a.scale;
+  __syncthreads();
+  for (int e = tid; e < a.H * Tq * Tk; e += ATT_THREADS) {
+    const int h = e / (Tq * Tk), i = (e / Tk) % Tq, j = e % Tk;
+    float s = -INFINITY;
+    if (!(a.causal && j > i)) {
+      const float* qp = sq + i * DP + h * hd;
+      const float* kp = sk + j * DP + h * hd;
+      float acc = 0.f;
+      for (int c = 0; c < hd; c += 4) {
+        float4 qv = *reinterpret_cast<const float4*>(qp + c), kv = *reinterpret_cast<const float4*>(kp + c);
+        acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+      }
+      s = acc * a.scale;
+    }
+    sp[(h * Tq + i) * (Tk + 1) + j] = s;
   }
-  __syncwarp();
-  if (lane < Tq) {
+  __syncthreads();
+  if (tid < a.H * Tq) {
+    float* row = sp + tid * (Tk + 1);
     float mx = -INFINITY;
-    for (int j = 0; j < Tk; ++j) mx = fmaxf(mx, sp[w][lane][j]);
+    for (int j = 0; j < Tk; ++j) mx = fmaxf(mx, row[j]);
     float sum = 0.f;
-    for (int j = 0; j < Tk; ++j) { float e = expf(sp[w][lane][j] - mx); sp[w][lane][j] = e; sum += e; }
-    float inv = 1.0f / sum;
-    for (int j = 0; j < Tk; ++j) sp[w][lane][j] *= inv;
+    for (int j = 0; j < Tk; ++j) { float ex = expf(row[j] - mx); row[j] = ex; sum += ex; }
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < Tk; ++j) row[j] *= inv;
   }
-  __syncwarp();
-  for (int e = lane; e < Tq * hd; e += 32) {
-    int i = e / hd, c = e % hd;
+  __syncthreads();
+  for (int e = tid; e < Tq * D; e += ATT_THREADS) {
+    const int i = e / D, col = e % D, h = col / hd;
+    const float* pr = sp + (h * Tq + i) * (Tk + 1);
     float o = 0.f;
-    for (int j = 0; j < Tk; ++j) o = fmaf(sp[w][i][j], sv[w][j][c], o);
-    size_t row = (size_t)(b * Tq + i);
-    if (a.y) a.y[row * a.ldy + h * hd + c] = o;
+    for (int j = 0; j < Tk; ++j) o = fmaf(pr[j], sv[j * DP + col], o);
+    const size_t row = (size_t)(b * Tq + i);
+    if (a.y) a.y[row * a.ldy + col] = o;
     if (a.y16) {
       __nv_bfloat16 hi, lo;
       split_bf16(o, hi, lo);
-      a.y16[row * a.ld16 + h * hd + c] = hi;
-      a.y16[row * a.ld16 + a.lo_off + h * hd + c] = lo;
+      a.y16[row * a.ld16 + col] = hi;
+      a.y16[row * a.ld16 + a.lo_off + col] = lo;
     }
   }
 }
@@ -289,6 +335,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(AttnArgs a) {
 // Sinusoidal sigma embedding: pe[r, :] = [sin(e f_k), cos(e f_k)], e = log(sigma_r)/4,
 // f_k = exp(-k ln(10000)/(half-1))      (mdtv_transformer.py:13-25, :238-244)
 __global__ void sigma_posemb_kernel(const float* __restrict__ sigma, int R, int d, float* __restrict__ pe) {
+  pdl_enter();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int half = d / 2;
   if (idx >= R * half) return;
@@ -317,6 +364,7 @@ struct ActEmbArgs {
   const float* W; const float* b; float* xh; float sigma_data; int precondition;
 };
 __global__ void action_embed_kernel(ActEmbArgs a) {
+  pdl_enter();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.M * a.d) return;
   int m = idx / a.d, n = idx % a.d;
@@ -358,6 +406,7 @@ struct HeadArgs {
 
 template <int VPL>
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const float* xr = a.xh + (size_t)warp * a.d;
@@ -456,6 +505,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 // MDT variant: add the learned positional embedding rows to the encoder input
 // (mdt_transformer.py:318-324): token 0 += pos[0], tokens 1.. += pos[goal_seq_len] (t = 1).
 __global__ void add_pos_emb_kernel(float* x, const float* pos, int B, int Tc, int d) {
+  pdl_enter();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * Tc * d) return;
   int c = idx % d, t = (idx / d) % Tc;
