@@ -65,6 +65,13 @@ struct GraphEntry { cudaGraphExec_t exec; int64_t kernels; };
 
 }  // namespace
 
+// workspace pointers of one (sub-)batch; a sampling call splits the batch into independent branches (samples never
+// interact), each with its own Work view, captured as parallel chains of the CUDA graph.
+struct Work {
+  float *in_goal, *in_state, *x, *x2, *dbuf, *gh, *xe, *ctx, *kv, *xh, *a, *qkv, *y, *hbuf, *q;
+  __nv_bfloat16 *a16, *y16, *h16;
+};
+
 struct MdtHandle {
   MdtConfig cfg;
   int device = 0;
@@ -87,6 +94,23 @@ struct MdtHandle {
   int mod_rows = 0;
 
   cudaStream_t cap_stream = nullptr;
+  static constexpr int MAX_BRANCHES = 8;
+  cudaStream_t branch_streams[MAX_BRANCHES] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES] = {};
+  int branches = 4;               // MDTB200_BRANCHES overrides
+
+  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16}; }
+  // view of samples [b0, ...): every buffer is row-indexed by sample (encoder rows reuse the decoder row offsets, Tc <= T)
+  Work slice(const Work& w, int b0) const {
+    const size_t r = (size_t)b0 * T, dd = d;
+    Work o = w;
+    o.in_goal += (size_t)b0 * cfg.goal_dim; o.in_state += (size_t)b0 * Ts * cfg.obs_dim;
+    o.x += r * A; o.x2 += r * A; o.dbuf += r * A; o.gh += (size_t)b0 * 2 * dd;
+    o.xe += r * dd; o.ctx += (size_t)b0 * Tc * dd; o.kv += (size_t)b0 * Tc * Ld * 2 * dd;
+    o.xh += r * dd; o.a += r * dd; o.qkv += r * 3 * dd; o.y += r * dd; o.hbuf += r * 4 * dd; o.q += r * dd;
+    if (o.a16) { o.a16 += r * 2 * dd; o.y16 += r * 2 * dd; o.h16 += r * 8 * dd; }
+    return o;
+  }
   std::map<GraphKey, GraphEntry> graphs;
   int64_t launches = 0;
   int64_t capture_count = 0;      // kernels launched while capturing
@@ -204,6 +228,17 @@ int launch_attn(MdtHandle* h, const float* q, int ldq, const float* k, const flo
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = h->d; a.y16 = y16; a.ld16 = 2 * h->d; a.lo_off = h->d;
   a.B = B; a.H = h->H; a.hd = h->hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
   a.scale = 1.0f / sqrtf((float)h->hd);
+  // shipped shapes run the compile-time specialised kernel (4 heads per CTA); anything else the generic one
+  const bool c = causal != 0;
+  #define ATT_CASE(HD, TQ, TK, CA)                                                                                  \
+    if (h->hd == HD && Tq == TQ && Tk == TK && c == (CA != 0) && h->H % 4 == 0) {                                   \
+      launch_pdl(attention_fixed_kernel<HD, TQ, TK, CA, 4>, dim3(B, h->H / 4), dim3(128), 0, st, a);                \
+      count_launch(h);                                                                                              \
+      return check_launch(h, "attention_fixed_kernel");                                                             \
+    }
+  ATT_CASE(48, 10, 10, 1) ATT_CASE(48, 10, 4, 1) ATT_CASE(48, 4, 4, 0)
+  ATT_CASE(64, 10, 10, 1) ATT_CASE(64, 10, 3, 1) ATT_CASE(64, 3, 3, 0)
+  #undef ATT_CASE
   launch_pdl(attention_kernel, dim3(B), dim3(ATT_THREADS), attention_smem_bytes(h->d, h->H, Tq, Tk), st, a);
   count_launch(h);
   return check_launch(h, "attention_kernel");
@@ -230,73 +265,80 @@ inline bool use_tc(const MdtHandle* h) { return h->cfg.precision != MDTB200_PREC
 
 // ------------------------------------------------------------------------------------------ network pieces
 
+// number of concurrent sub-batch chains for a sampling call: sub-batches of >= 32 samples, rows a multiple of 128 if possible
+int branch_count(const MdtHandle* h, int B) {
+  int nb = h->branches < 1 ? 1 : (h->branches > MdtHandle::MAX_BRANCHES ? MdtHandle::MAX_BRANCHES : h->branches);
+  while (nb > 1 && B / nb < 32) --nb;
+  return nb;
+}
+
 // cross-attention K/V of every decoder layer from the context: kv[Mc, L*2d] = ctx . Wkv_all^T + b
-int compute_kv(MdtHandle* h, int B, cudaStream_t st, bool ctx_split_valid = false) {
+int compute_kv(MdtHandle* h, const Work& k, int B, cudaStream_t st, bool ctx_split_valid = false) {
   Gemm g;
-  g.A = h->ctx; g.lda = h->d; g.W = h->w.wkv_all; g.bias = h->w.bkv_all; g.C = h->kv; g.ldc = h->Ld * 2 * h->d;
+  g.A = k.ctx; g.lda = h->d; g.W = h->w.wkv_all; g.bias = h->w.bkv_all; g.C = k.kv; g.ldc = h->Ld * 2 * h->d;
   g.M = B * h->Tc; g.N = h->Ld * 2 * h->d; g.K = h->d;
-  if (ctx_split_valid) { g.A16 = h->a16; g.lda16 = 2 * h->d; g.W16 = h->w.wkv_all16; }
+  if (ctx_split_valid) { g.A16 = k.a16; g.lda16 = 2 * h->d; g.W16 = h->w.wkv_all16; }
   return gemm(h, g, st);
 }
 
 // forward_enc_only (mdtv_transformer.py:213-222; mdt_transformer.py:211-229 for the MDT variant)
-int encoder(MdtHandle* h, const float* goal, const float* state, int modality, int B, cudaStream_t st) {
+int encoder(MdtHandle* h, const Work& k, const float* goal, const float* state, int modality, int B, cudaStream_t st) {
   const int d = h->d, Tc = h->Tc, Ts = h->Ts, Mc = B * Tc;
   const Weights& w = h->w;
   const bool lang = modality == MDTB200_MODALITY_LANG && w.lang0_w != nullptr;
   {  // goal MLP: Linear(goal_dim, 2d) -> GELU -> Linear(2d, d), written to context token 0
     Gemm g;
     g.A = goal; g.lda = h->cfg.goal_dim; g.W = lang ? w.lang0_w : w.goal0_w; g.bias = lang ? w.lang0_b : w.goal0_b;
-    g.C = h->gh; g.ldc = 2 * d; g.M = B; g.N = 2 * d; g.K = h->cfg.goal_dim; g.epi = EPI_GELU;
+    g.C = k.gh; g.ldc = 2 * d; g.M = B; g.N = 2 * d; g.K = h->cfg.goal_dim; g.epi = EPI_GELU;
     TRY(gemm(h, g, st));
     Gemm g2;
-    g2.A = h->gh; g2.lda = 2 * d; g2.W = lang ? w.lang2_w : w.goal2_w; g2.bias = lang ? w.lang2_b : w.goal2_b;
-    g2.C = h->xe; g2.ldc = d; g2.M = B; g2.N = d; g2.K = 2 * d; g2.gi = 1; g2.go = Tc; g2.goff = 0;
+    g2.A = k.gh; g2.lda = 2 * d; g2.W = lang ? w.lang2_w : w.goal2_w; g2.bias = lang ? w.lang2_b : w.goal2_b;
+    g2.C = k.xe; g2.ldc = d; g2.M = B; g2.N = d; g2.K = 2 * d; g2.gi = 1; g2.go = Tc; g2.goff = 0;
     TRY(gemm(h, g2, st));
   }
   if (h->cfg.variant == MDTB200_VARIANT_MDTV) {  // tok_emb on the n_state_tokens Voltron tokens -> context tokens 1..
     Gemm g;
-    g.A = state; g.lda = h->cfg.obs_dim; g.W = w.tok_w; g.bias = w.tok_b; g.C = h->xe; g.ldc = d;
+    g.A = state; g.lda = h->cfg.obs_dim; g.W = w.tok_w; g.bias = w.tok_b; g.C = k.xe; g.ldc = d;
     g.M = B * Ts; g.N = d; g.K = h->cfg.obs_dim; g.gi = Ts; g.go = Tc; g.goff = 1;
     TRY(gemm(h, g, st));
   } else {  // MDT: token 1 = tok_emb(static), token 2 = incam_embed(gripper); then learned pos_emb
     for (int t = 0; t < 2; ++t) {
       Gemm g;
       g.A = state + (size_t)t * h->cfg.obs_dim; g.lda = 2 * h->cfg.obs_dim; g.W = t == 0 ? w.tok_w : w.incam_w; g.bias = t == 0 ? w.tok_b : w.incam_b;
-      g.C = h->xe; g.ldc = d; g.M = B; g.N = d; g.K = h->cfg.obs_dim; g.gi = 1; g.go = Tc; g.goff = 1 + t;
+      g.C = k.xe; g.ldc = d; g.M = B; g.N = d; g.K = h->cfg.obs_dim; g.gi = 1; g.go = Tc; g.goff = 1 + t;
       TRY(gemm(h, g, st));
     }
     int n = Mc * d;
-    launch_pdl(add_pos_emb_kernel, dim3((n + 255) / 256), dim3(256), 0, st, h->xe, w.pos_emb, B, Tc, d);
+    launch_pdl(add_pos_emb_kernel, dim3((n + 255) / 256), dim3(256), 0, st, k.xe, w.pos_emb, B, Tc, d);
     count_launch(h);
     TRY(check_launch(h, "add_pos_emb_kernel"));
   }
   const bool tcp = use_tc(h);
   for (int l = 0; l < h->Le; ++l) {  // Block.forward, transformer_blocks.py:209-214
     const EncLayerW& L = w.enc[l];
-    TRY(launch_ln(h, h->xe, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln1_w, L.ln1_b, nullptr, nullptr, 0, Mc, st));
+    TRY(launch_ln(h, k.xe, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln1_w, L.ln1_b, nullptr, nullptr, 0, Mc, st));
     Gemm g;
-    g.A = h->a; g.lda = d; g.A16 = h->a16; g.lda16 = 2 * d; g.W = L.wqkv; g.W16 = L.wqkv16; g.bias = L.bqkv; g.C = h->qkv; g.ldc = 3 * d;
+    g.A = k.a; g.lda = d; g.A16 = k.a16; g.lda16 = 2 * d; g.W = L.wqkv; g.W16 = L.wqkv16; g.bias = L.bqkv; g.C = k.qkv; g.ldc = 3 * d;
     g.M = Mc; g.N = 3 * d; g.K = d;
     TRY(gemm(h, g, st));
-    TRY(launch_attn(h, h->qkv, 3 * d, h->qkv + d, h->qkv + 2 * d, 3 * d, tcp ? nullptr : h->y, tcp ? h->y16 : nullptr, B, Tc, Tc, 0, st));
+    TRY(launch_attn(h, k.qkv, 3 * d, k.qkv + d, k.qkv + 2 * d, 3 * d, tcp ? nullptr : k.y, tcp ? k.y16 : nullptr, B, Tc, Tc, 0, st));
     Gemm o;
-    o.A = h->y; o.lda = d; o.A16 = h->y16; o.lda16 = 2 * d; o.W = L.wo; o.W16 = L.wo16; o.bias = L.bo; o.C = h->xe; o.ldc = d; o.R = h->xe; o.ldr = d;
+    o.A = k.y; o.lda = d; o.A16 = k.y16; o.lda16 = 2 * d; o.W = L.wo; o.W16 = L.wo16; o.bias = L.bo; o.C = k.xe; o.ldc = d; o.R = k.xe; o.ldr = d;
     o.M = Mc; o.N = d; o.K = d; o.epi = EPI_RES;
     TRY(gemm(h, o, st));
-    TRY(launch_ln(h, h->xe, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln2_w, L.ln2_b, nullptr, nullptr, 0, Mc, st));
+    TRY(launch_ln(h, k.xe, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln2_w, L.ln2_b, nullptr, nullptr, 0, Mc, st));
     Gemm f;
-    f.A = h->a; f.lda = d; f.A16 = h->a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
-    f.C = tcp ? nullptr : h->hbuf; f.ldc = 4 * d; f.C16 = tcp ? h->h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
+    f.A = k.a; f.lda = d; f.A16 = k.a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
+    f.C = tcp ? nullptr : k.hbuf; f.ldc = 4 * d; f.C16 = tcp ? k.h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
     f.M = Mc; f.N = 4 * d; f.K = d; f.epi = EPI_GELU;
     TRY(gemm(h, f, st));
     Gemm p;
-    p.A = h->hbuf; p.lda = 4 * d; p.A16 = h->h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = h->xe; p.ldc = d; p.R = h->xe; p.ldr = d;
+    p.A = k.hbuf; p.lda = 4 * d; p.A16 = k.h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = k.xe; p.ldc = d; p.R = k.xe; p.ldr = d;
     p.M = Mc; p.N = d; p.K = 4 * d; p.epi = EPI_RES;
     TRY(gemm(h, p, st));
   }
-  TRY(launch_ln(h, h->xe, h->ctx, tcp ? h->a16 : nullptr, w.enc_ln_w, w.enc_ln_b, nullptr, nullptr, 0, Mc, st));
-  TRY(compute_kv(h, B, st, tcp));
+  TRY(launch_ln(h, k.xe, k.ctx, tcp ? k.a16 : nullptr, w.enc_ln_w, w.enc_ln_b, nullptr, nullptr, 0, Mc, st));
+  TRY(compute_kv(h, k, B, st, tcp));
   h->ctx_B = B;
   return 0;
 }
@@ -325,7 +367,7 @@ int sigma_path(MdtHandle* h, const float* sigma, int R, cudaStream_t st) {
 //   x_in     actions the network sees (before c_in scaling)
 //   mod      AdaLN rows for this evaluation; mod_stride = 0 -> one row shared by the batch
 //   sigma/sigma_stride   per-sample sigma for the c_in scaling (stride 0 -> shared)
-int decoder_eval(MdtHandle* h, const float* x_in, const float* mod, int mod_stride, const float* sigma, int sigma_stride,
+int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mod, int mod_stride, const float* sigma, int sigma_stride,
                  int precondition, int B, HeadArgs head, cudaStream_t st) {
   const int d = h->d, T = h->T, Tc = h->Tc, M = B * T;
   const Weights& w = h->w;
@@ -333,7 +375,7 @@ int decoder_eval(MdtHandle* h, const float* x_in, const float* mod, int mod_stri
   {
     ActEmbArgs a{};
     a.x = x_in; a.sigma = sigma; a.sigma_stride = sigma_stride; a.T = T; a.A = h->A; a.d = d; a.M = M;
-    a.W = w.ae_w; a.b = w.ae_b; a.xh = h->xh; a.sigma_data = h->cfg.sigma_data; a.precondition = precondition;
+    a.W = w.ae_w; a.b = w.ae_b; a.xh = k.xh; a.sigma_data = h->cfg.sigma_data; a.precondition = precondition;
     int n = M * d;
     launch_pdl(action_embed_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a);
     count_launch(h);
@@ -344,50 +386,49 @@ int decoder_eval(MdtHandle* h, const float* x_in, const float* mod, int mod_stri
     const DecLayerW& L = w.dec[l];
     const float* ml = mod + (size_t)l * 6 * d;   // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
     // x += gate_msa * SelfAttn_causal(shift_msa + LN1(x) * scale_msa)
-    TRY(launch_ln(h, h->xh, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln1_w, L.ln1_b, ml, ml + d, mod_stride, M, st));
+    TRY(launch_ln(h, k.xh, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln1_w, L.ln1_b, ml, ml + d, mod_stride, M, st));
     Gemm g;
-    g.A = h->a; g.lda = d; g.A16 = h->a16; g.lda16 = 2 * d; g.W = L.wqkv; g.W16 = L.wqkv16; g.bias = L.bqkv; g.C = h->qkv; g.ldc = 3 * d; g.M = M; g.N = 3 * d; g.K = d;
+    g.A = k.a; g.lda = d; g.A16 = k.a16; g.lda16 = 2 * d; g.W = L.wqkv; g.W16 = L.wqkv16; g.bias = L.bqkv; g.C = k.qkv; g.ldc = 3 * d; g.M = M; g.N = 3 * d; g.K = d;
     TRY(gemm(h, g, st));
-    TRY(launch_attn(h, h->qkv, 3 * d, h->qkv + d, h->qkv + 2 * d, 3 * d, tcp ? nullptr : h->y, tcp ? h->y16 : nullptr, B, T, T, 1, st));
+    TRY(launch_attn(h, k.qkv, 3 * d, k.qkv + d, k.qkv + 2 * d, 3 * d, tcp ? nullptr : k.y, tcp ? k.y16 : nullptr, B, T, T, 1, st));
     Gemm o;
-    o.A = h->y; o.lda = d; o.A16 = h->y16; o.lda16 = 2 * d; o.W = L.wo; o.W16 = L.wo16; o.bias = L.bo; o.C = h->xh; o.ldc = d; o.R = h->xh; o.ldr = d;
+    o.A = k.y; o.lda = d; o.A16 = k.y16; o.lda16 = 2 * d; o.W = L.wo; o.W16 = L.wo16; o.bias = L.bo; o.C = k.xh; o.ldc = d; o.R = k.xh; o.ldr = d;
     o.gate = ml + 2 * d; o.gate_stride = mod_stride; o.rows_per_group = T; o.M = M; o.N = d; o.K = d; o.epi = EPI_RES_GATE;
     TRY(gemm(h, o, st));
     // x += CrossAttn_causal-top-left(LN3(x), ctx)       (ln3 is nn.LayerNorm with bias)
-    TRY(launch_ln(h, h->xh, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln3_w, L.ln3_b, nullptr, nullptr, 0, M, st));
+    TRY(launch_ln(h, k.xh, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln3_w, L.ln3_b, nullptr, nullptr, 0, M, st));
     Gemm cq;
-    cq.A = h->a; cq.lda = d; cq.A16 = h->a16; cq.lda16 = 2 * d; cq.W = L.wq; cq.W16 = L.wq16; cq.bias = L.bq; cq.C = h->q; cq.ldc = d; cq.M = M; cq.N = d; cq.K = d;
+    cq.A = k.a; cq.lda = d; cq.A16 = k.a16; cq.lda16 = 2 * d; cq.W = L.wq; cq.W16 = L.wq16; cq.bias = L.bq; cq.C = k.q; cq.ldc = d; cq.M = M; cq.N = d; cq.K = d;
     TRY(gemm(h, cq, st));
-    TRY(launch_attn(h, h->q, d, h->kv + (size_t)l * 2 * d, h->kv + (size_t)l * 2 * d + d, kvld, tcp ? nullptr : h->y, tcp ? h->y16 : nullptr, B, T, Tc, 1, st));
+    TRY(launch_attn(h, k.q, d, k.kv + (size_t)l * 2 * d, k.kv + (size_t)l * 2 * d + d, kvld, tcp ? nullptr : k.y, tcp ? k.y16 : nullptr, B, T, Tc, 1, st));
     Gemm co;
-    co.A = h->y; co.lda = d; co.A16 = h->y16; co.lda16 = 2 * d; co.W = L.wco; co.W16 = L.wco16; co.bias = L.bco; co.C = h->xh; co.ldc = d; co.R = h->xh; co.ldr = d;
+    co.A = k.y; co.lda = d; co.A16 = k.y16; co.lda16 = 2 * d; co.W = L.wco; co.W16 = L.wco16; co.bias = L.bco; co.C = k.xh; co.ldc = d; co.R = k.xh; co.ldr = d;
     co.M = M; co.N = d; co.K = d; co.epi = EPI_RES;
     TRY(gemm(h, co, st));
     // x += gate_mlp * MLP(shift_mlp + LN2(x) * scale_mlp)
-    TRY(launch_ln(h, h->xh, tcp ? nullptr : h->a, tcp ? h->a16 : nullptr, L.ln2_w, L.ln2_b, ml + 3 * d, ml + 4 * d, mod_stride, M, st));
+    TRY(launch_ln(h, k.xh, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln2_w, L.ln2_b, ml + 3 * d, ml + 4 * d, mod_stride, M, st));
     Gemm f;
-    f.A = h->a; f.lda = d; f.A16 = h->a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
-    f.C = tcp ? nullptr : h->hbuf; f.ldc = 4 * d; f.C16 = tcp ? h->h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
+    f.A = k.a; f.lda = d; f.A16 = k.a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
+    f.C = tcp ? nullptr : k.hbuf; f.ldc = 4 * d; f.C16 = tcp ? k.h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
     f.M = M; f.N = 4 * d; f.K = d; f.epi = EPI_GELU;
     TRY(gemm(h, f, st));
     Gemm p;
-    p.A = h->hbuf; p.lda = 4 * d; p.A16 = h->h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = h->xh; p.ldc = d; p.R = h->xh; p.ldr = d;
+    p.A = k.hbuf; p.lda = 4 * d; p.A16 = k.h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = k.xh; p.ldc = d; p.R = k.xh; p.ldr = d;
     p.gate = ml + 5 * d; p.gate_stride = mod_stride; p.rows_per_group = T; p.M = M; p.N = d; p.K = 4 * d; p.epi = EPI_RES_GATE;
     TRY(gemm(h, p, st));
   }
-  head.xh = h->xh; head.lnw = w.dec_ln_w; head.lnb = w.dec_ln_b; head.W = w.ap_w; head.bias = w.ap_b;
+  head.xh = k.xh; head.lnw = w.dec_ln_w; head.lnb = w.dec_ln_b; head.W = w.ap_w; head.bias = w.ap_b;
   head.M = M; head.d = d; head.A = h->A; head.T = T; head.sigma_data = h->cfg.sigma_data;
   return launch_head(h, head, st);
 }
 
-// the whole sampling call on the handle's static buffers (captured into a graph by mdtb200_sample)
-int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cudaStream_t st) {
-  TRY(encoder(h, h->in_goal, h->in_state, modality, B, st));
-  TRY(sigma_path(h, h->sigmas, n_steps, st));   // one AdaLN row per step: sigma is shared by the batch
+// sampler iterations of one branch (sub-batch) on its own stream
+int sample_steps(MdtHandle* h, const Work& k, int sampler, int n_steps, int modality, int B, cudaStream_t st) {
+  TRY(encoder(h, k, k.in_goal, k.in_state, modality, B, st));
   const size_t mrow = (size_t)h->Ld * 6 * h->d;
   for (int i = 0; i < n_steps; ++i) {
     HeadArgs hd{};
-    hd.x_in = h->x; hd.x_state = h->x; hd.x_aux = h->x2; hd.dbuf = h->dbuf; hd.sigmas = h->sigmas; hd.step = i; hd.n_steps = n_steps;
+    hd.x_in = k.x; hd.x_state = k.x; hd.x_aux = k.x2; hd.dbuf = k.dbuf; hd.sigmas = h->sigmas; hd.step = i; hd.n_steps = n_steps;
     switch (sampler) {
       case MDTB200_SAMPLER_DDIM: hd.mode = HEAD_DDIM; break;
       case MDTB200_SAMPLER_EULER: hd.mode = HEAD_EULER; break;
@@ -395,14 +436,36 @@ int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cud
       case MDTB200_SAMPLER_DPMPP_2M: hd.mode = HEAD_DPMPP2M; break;
       default: return fail(h, MDTB200_EINVAL, "unknown sampler %d", sampler);
     }
-    TRY(decoder_eval(h, h->x, h->mod + i * mrow, 0, h->sigmas + i, 0, 1, B, hd, st));
+    TRY(decoder_eval(h, k, k.x, h->mod + i * mrow, 0, h->sigmas + i, 0, 1, B, hd, st));
     if (sampler == MDTB200_SAMPLER_HEUN && i + 1 < n_steps) {   // 2nd-order correction; the last step (sigma_next = 0) is Euler
       HeadArgs h2 = hd;
-      h2.mode = HEAD_HEUN2; h2.x_in = h->x2;
-      TRY(decoder_eval(h, h->x2, h->mod + (i + 1) * mrow, 0, h->sigmas + i + 1, 0, 1, B, h2, st));
+      h2.mode = HEAD_HEUN2; h2.x_in = k.x2;
+      TRY(decoder_eval(h, k, k.x2, h->mod + (i + 1) * mrow, 0, h->sigmas + i + 1, 0, 1, B, h2, st));
     }
   }
   return 0;
+}
+
+// The whole sampling call on the handle's static buffers (captured into a graph by mdtb200_sample).  The AdaLN
+// table of all steps is computed once; then the batch is cut into `branches` independent sub-batches whose kernel
+// chains run concurrently (fork/join through events -> parallel branches of the captured graph): every kernel of this
+// path is latency- rather than throughput-bound at B=256, so concurrent chains fill the SMs the others leave idle.
+int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cudaStream_t st) {
+  TRY(sigma_path(h, h->sigmas, n_steps, st));   // one AdaLN row per step: sigma is shared by the batch
+  const int nb = branch_count(h, B);
+  const Work base = h->work();
+  if (nb <= 1) return sample_steps(h, base, sampler, n_steps, modality, B, st);
+  CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+  int rc = 0;
+  for (int s = 0; s < nb && !rc; ++s) {
+    const int b0 = (int)((long long)B * s / nb), b1 = (int)((long long)B * (s + 1) / nb);
+    cudaStream_t bs = h->branch_streams[s];
+    CUDA_TRY(h, cudaStreamWaitEvent(bs, h->ev_fork, 0));
+    rc = sample_steps(h, h->slice(base, b0), sampler, n_steps, modality, b1 - b0, bs);
+    CUDA_TRY(h, cudaEventRecord(h->ev_join[s], bs));
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[s], 0));
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------ weights
@@ -648,6 +711,12 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
     }
   }
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(h, MDTB200_ECUDA, "cudaStreamCreate failed"); return bail(MDTB200_ECUDA); }
+  for (int i = 0; i < MdtHandle::MAX_BRANCHES; ++i) {
+    if (cudaStreamCreateWithFlags(&h->branch_streams[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { fail(h, MDTB200_ECUDA, "stream/event creation failed"); return bail(MDTB200_ECUDA); }
+  }
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { fail(h, MDTB200_ECUDA, "event creation failed"); return bail(MDTB200_ECUDA); }
+  if (const char* e = getenv("MDTB200_BRANCHES")) h->branches = atoi(e);
   *out = h;
   return 0;
 }
@@ -656,6 +725,11 @@ MDTB200_API void mdtb200_destroy(MdtHandle* h) {
   if (!h) return;
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (int i = 0; i < MdtHandle::MAX_BRANCHES; ++i) {
+    if (h->branch_streams[i]) cudaStreamDestroy(h->branch_streams[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -687,7 +761,7 @@ MDTB200_API int mdtb200_encode(MdtHandle* h, const float* goal, const float* sta
   TRY(check_ready(h, B));
   if (!goal || !state) return fail(h, MDTB200_EINVAL, "encode: null input");
   cudaStream_t st = (cudaStream_t)stream;
-  TRY(encoder(h, goal, state, modality, B, st));
+  TRY(encoder(h, h->work(), goal, state, modality, B, st));
   if (ctx_out) CUDA_TRY(h, cudaMemcpyAsync(ctx_out, h->ctx, (size_t)B * h->Tc * h->d * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
@@ -704,7 +778,7 @@ MDTB200_API int mdtb200_set_context(MdtHandle* h, const float* ctx, int B, void*
     count_launch(h);
     TRY(check_launch(h, "split_weights_kernel"));
   }
-  TRY(compute_kv(h, B, st, tcp));
+  TRY(compute_kv(h, h->work(), B, st, tcp));
   h->ctx_B = B;
   return 0;
 }
@@ -717,7 +791,7 @@ MDTB200_API int mdtb200_denoise(MdtHandle* h, const float* x, const float* sigma
   TRY(sigma_path(h, sigma, B, st));
   HeadArgs hd{};
   hd.mode = precondition ? HEAD_DENOISE : HEAD_RAW; hd.x_in = x; hd.out = out; hd.sigma = sigma; hd.sigma_stride = 1;
-  return decoder_eval(h, x, h->mod, h->Ld * 6 * h->d, sigma, 1, precondition, B, hd, st);
+  return decoder_eval(h, h->work(), x, h->mod, h->Ld * 6 * h->d, sigma, 1, precondition, B, hd, st);
 }
 
 static int get_graph(MdtHandle* h, int sampler, int n_steps, int modality, int B, GraphEntry** out) {

@@ -172,7 +172,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_enter();      // prologue above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_wait();       // prologue above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -223,6 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int e = warp - 4;                 // warp e owns TMEM lanes [32e, 32e+32)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    pdl_trigger();    // all MMAs of this CTA are done: the next kernel may start its prologue while we drain TMEM
     const int row = m0 + e * 32 + lane;
     const bool valid = row < p.M;
     const size_t grow = valid ? (size_t)(row / p.rows_per_group) * p.gate_stride : 0;
@@ -359,7 +360,8 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE) return "unsupported epilogue";
   // tile-N choice: 128 columns when that still yields >= ~1 wave of CTAs on 148 SMs, else 64
   const int mt = (g.M + BM - 1) / BM;
-  const int bn = (g.N % 128 == 0 && mt * (g.N / 128) >= 120) ? 128 : 64;
+  const int bn = (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
+  (void)mt;
   CUtensorMap ta, tw;
   const char* e;
   if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;

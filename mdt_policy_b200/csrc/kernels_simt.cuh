@@ -32,10 +32,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // Programmatic dependent launch (PDL): every kernel first lets its dependents start launching (their prologue
 // overlaps our tail), then waits until all prerequisite grids have completed and flushed before touching memory.
-__device__ __forceinline__ void pdl_enter() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
 // ------------------------------------------------------------------------------------------
 // activations (exact variants, matching ATen)
@@ -327,6 +326,85 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
       split_bf16(o, hi, lo);
       a.y16[row * a.ld16 + col] = hi;
       a.y16[row * a.ld16 + a.lo_off + col] = lo;
+    }
+  }
+}
+
+// Compile-time specialisation of the same algorithm for the shipped shapes (all index arithmetic folds to
+// constants, loops unroll).  One CTA handles HC heads of one sample: grid = (B, H / HC), 128 threads.
+template <int HD, int TQ, int TK, int CAUSAL, int HC>
+__global__ void __launch_bounds__(128) attention_fixed_kernel(AttnArgs a) {
+  constexpr int DC = HC * HD, DP = DC + 4, D4 = DC / 4, NT = 128;
+  __shared__ __align__(16) float sq[TQ * DP];
+  __shared__ __align__(16) float sk[TK * DP];
+  __shared__ __align__(16) float sv[TK * DP];
+  __shared__ float sp[HC * TQ * (TK + 1)];
+  pdl_enter();
+  const int b = blockIdx.x, c0 = blockIdx.y * DC, tid = threadIdx.x;
+#pragma unroll
+  for (int e = tid; e < TQ * D4; e += NT) {
+    const int r = e / D4, c = (e % D4) * 4;
+    *reinterpret_cast<float4*>(sq + r * DP + c) = *reinterpret_cast<const float4*>(a.q + (size_t)(b * TQ + r) * a.ldq + c0 + c);
+  }
+#pragma unroll
+  for (int e = tid; e < TK * D4; e += NT) {
+    const int r = e / D4, c = (e % D4) * 4;
+    *reinterpret_cast<float4*>(sk + r * DP + c) = *reinterpret_cast<const float4*>(a.k + (size_t)(b * TK + r) * a.ldkv + c0 + c);
+    *reinterpret_cast<float4*>(sv + r * DP + c) = *reinterpret_cast<const float4*>(a.v + (size_t)(b * TK + r) * a.ldkv + c0 + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = tid; e < HC * TQ * TK; e += NT) {
+    const int h = e / (TQ * TK), i = (e / TK) % TQ, j = e % TK;
+    float s = -INFINITY;
+    if (!(CAUSAL && j > i)) {
+      const float* qp = sq + i * DP + h * HD;
+      const float* kp = sk + j * DP + h * HD;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        float4 qv = *reinterpret_cast<const float4*>(qp + c), kv = *reinterpret_cast<const float4*>(kp + c);
+        acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+      }
+      s = acc * a.scale;
+    }
+    sp[(h * TQ + i) * (TK + 1) + j] = s;
+  }
+  __syncthreads();
+  if (tid < HC * TQ) {
+    float* row = sp + tid * (TK + 1);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) mx = fmaxf(mx, row[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) { float ex = expf(row[j] - mx); row[j] = ex; sum += ex; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) row[j] *= inv;
+  }
+  __syncthreads();
+  // P.V: each thread produces 4 consecutive output columns of one query row
+#pragma unroll
+  for (int e = tid; e < TQ * D4; e += NT) {
+    const int i = e / D4, col = (e % D4) * 4, h = col / HD;
+    const float* pr = sp + (h * TQ + i) * (TK + 1);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < TK; ++j) {
+      const float pj = pr[j];
+      const float4 vv = *reinterpret_cast<const float4*>(sv + j * DP + col);
+      o[0] = fmaf(pj, vv.x, o[0]); o[1] = fmaf(pj, vv.y, o[1]); o[2] = fmaf(pj, vv.z, o[2]); o[3] = fmaf(pj, vv.w, o[3]);
+    }
+    const size_t row = (size_t)(b * TQ + i);
+    if (a.y) *reinterpret_cast<float4*>(a.y + row * a.ldy + c0 + col) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.y16) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) split_bf16(o[t], hi[t], lo[t]);
+      __nv_bfloat16* ph = a.y16 + row * a.ld16 + c0 + col;
+      *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
+      *reinterpret_cast<uint2*>(ph + a.lo_off) = *reinterpret_cast<uint2*>(lo);
     }
   }
 }
