@@ -187,9 +187,9 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: bench.py (impl=ours) measures the CUDA path only"}))
         return 1
-    rank, local_rank, world = D.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    rank, local_rank, world = D.init_from_env("nccl")
 
     from mdt_policy_b200 import GCDenoiser, DenoiseAgent
     from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs

@@ -33,7 +33,10 @@ def shard_range(total: int, rank: int, world: int):
 
 def barrier():
     if dist.is_available() and dist.is_initialized():
-        dist.barrier()
+        if dist.get_backend() == "nccl":
+            dist.barrier(device_ids=[torch.cuda.current_device()])
+        else:
+            dist.barrier()
 
 
 def aggregate_throughput(local_units: float, local_seconds: float, device="cpu"):
