@@ -6,8 +6,8 @@
 // (cp.async.bulk.tensor, SWIZZLE_128B) into a multi-stage shared-memory ring; one elected thread issues
 // tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) with the fp32 accumulator in TMEM; with PASSES == 3
 // each k-block issues hi*hi + lo*hi + hi*lo into the same accumulator (~2^-17 relative operand error, see
-// tools/emulate_split_precision.py), with PASSES == 1 only hi*hi (plain bf16).  Warp roles (256 threads):
-//   warp 0  TMA producer      warp 1  MMA issuer      warp 2  TMEM allocator      warps 4-7  epilogue
+// tools/emulate_split_precision.py), with PASSES == 1 only hi*hi (plain bf16).  Warp roles (512 threads):
+//   warp 0  TMA producer      warp 1  MMA issuer      warp 2  TMEM allocator      all 16 warps: epilogue
 // Epilogue (TMEM -> registers via tcgen05.ld 32x32b): + bias, GELU(erf), residual, AdaLN gate, then fp32 store
 // and/or a split-bf16 store that directly produces the next GEMM's A operand.
 #pragma once
@@ -26,13 +26,14 @@ namespace mdt { namespace tc {
 constexpr int BM = 128;        // UMMA M (rows of A per CTA)
 constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;       // 16 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator; all 16 run the epilogue
 
 struct TcGemm {
   const __nv_bfloat16* A16; int lda16; const __nv_bfloat16* W16; const float* bias;
   float* C; int ldc; __nv_bfloat16* C16; int ldc16; int lo_off;
   const float* R; int ldr; const float* gate; int gate_stride; int rows_per_group;
   int M, N, K, epi, passes;
+  unsigned long long* trace;
 };
 
 struct TcParams {
@@ -40,7 +41,15 @@ struct TcParams {
   float* C; int ldc; __nv_bfloat16* C16; int ldc16; int lo_off;
   const float* R; int ldr; const float* gate; int gate_stride; int rows_per_group;
   int M, N, K, epi;
+  unsigned long long* trace;   // optional (tests): per-CTA globaltimer stamps [cta][8]
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot) do { if (p.trace) p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); } while (0)
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,6 +110,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -135,14 +153,17 @@ struct SmemLayout {
   static constexpr int A_TILE = BM * BK * 2;                 // 16 KB
   static constexpr int W_TILE = BN * BK * 2;
   static constexpr int STAGE = (PASSES == 3 ? 2 : 1) * (A_TILE + W_TILE);
+  // one CTA per SM with the deepest ring that fits: the operand stream is bound by per-SM ingest (~100 GB/s/SM measured), and
+  // 2-stage / 2-CTA-per-SM variants measured 9 % slower end to end (profiles/r01_experiments.md)
   static constexpr int STAGES = (PASSES == 3) ? (BN == 128 ? 3 : 4) : (BN == 128 ? 5 : 6);
+  static constexpr int MIN_CTAS = 1;
   static constexpr int BAR_OFF = STAGES * STAGE;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;         // barriers + tmem slot, + slack for 1024-B alignment
 };
 
 // ------------------------------------------------------------------------------------------ the kernel
 template <int BN, int PASSES>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, SmemLayout<BN, PASSES>::MIN_CTAS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   using L = SmemLayout<BN, PASSES>;
   extern __shared__ uint8_t smem_raw[];
@@ -157,6 +178,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = p.K / BK;
+  if (threadIdx.x == 0) TC_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -173,6 +195,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();       // prologue above overlapped the previous kernel's tail; its results are visible from here on
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -200,6 +223,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / L::STAGES) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (kb == 0) TC_STAMP(2);
+        if (kb == nkb - 1) TC_STAMP(3);
         const uint32_t st = sbase + s * L::STAGE;
         const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + L::A_TILE);
         const uint64_t a_lo = make_smem_desc(st + L::A_TILE + L::W_TILE), w_lo = make_smem_desc(st + 2 * L::A_TILE + L::W_TILE);
@@ -218,68 +243,92 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       umma_commit(tmem_full);               // accumulator complete
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int e = warp - 4;                 // warp e owns TMEM lanes [32e, 32e+32)
+  }
+  __syncwarp();
+  {
+    // ===== epilogue: TMEM -> registers -> global, by ALL 16 warps =====
+    // warp w may only touch TMEM lanes [32 (w % 4), +32): the four warps of a lane quarter split the BN columns.
+    const int q = warp & 3, grp = warp >> 2;
+    constexpr int CPW = BN / (THREADS / 128);            // columns per warp: 32 (BN = 128) or 16 (BN = 64)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     pdl_trigger();    // all MMAs of this CTA are done: the next kernel may start its prologue while we drain TMEM
-    const int row = m0 + e * 32 + lane;
-    const bool valid = row < p.M;
-    const size_t grow = valid ? (size_t)(row / p.rows_per_group) * p.gate_stride : 0;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(c * 32), v);
-      if (!valid) continue;
-      const int nb = n0 + c * 32;
-      float o[32];
+    if (threadIdx.x == 0) TC_STAMP(4);
+    // phase A (thread = accumulator row): TMEM -> +bias -> activation -> fp32 staging tile in the (now idle) pipeline smem
+    constexpr int SP = BN + 4;                             // padded row stride (floats) of the staging tile
+    float* stage = reinterpret_cast<float*>(smem);
+    {
+      const int r = q * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-      if (p.bias) {
+      for (int c = 0; c < CPW / 16; ++c) {
+        const int col = grp * CPW + c * 16;
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+        float o[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j);
-          o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
-        }
-      }
-      if (p.epi == EPI_GELU) {
+        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = gelu_erf(o[j]);
-      } else if (p.epi == EPI_RES || p.epi == EPI_RES_GATE) {
-        const float* rr = p.R + (size_t)row * p.ldr + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 r = *reinterpret_cast<const float4*>(rr + j);
-          if (p.epi == EPI_RES_GATE) {
-            float4 g = *reinterpret_cast<const float4*>(p.gate + grow + nb + j);
-            o[j] = r.x + g.x * o[j]; o[j + 1] = r.y + g.y * o[j + 1]; o[j + 2] = r.z + g.z * o[j + 2]; o[j + 3] = r.w + g.w * o[j + 3];
-          } else {
-            o[j] += r.x; o[j + 1] += r.y; o[j + 2] += r.z; o[j + 3] += r.w;
+          for (int j = 0; j < 16; j += 4) {
+            float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + col + j);
+            o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
           }
+        }
+        if (p.epi == EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = gelu_erf_fast(o[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(stage + r * SP + col + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // phase B (coalesced): consecutive threads own consecutive 8-column groups of a row -> full-line global loads/stores
+    constexpr int GPR = BN / 8;                            // 8-column groups per row
+    for (int idx = threadIdx.x; idx < BM * GPR; idx += THREADS) {
+      const int r = idx / GPR, cg = (idx % GPR) * 8;
+      const int row = m0 + r;
+      if (row >= p.M) continue;
+      const int nb = n0 + cg;
+      float o[8];
+      {
+        const float4 a = *reinterpret_cast<const float4*>(stage + r * SP + cg);
+        const float4 b = *reinterpret_cast<const float4*>(stage + r * SP + cg + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+      }
+      if (p.epi == EPI_RES || p.epi == EPI_RES_GATE) {
+        const float* rr = p.R + (size_t)row * p.ldr + nb;
+        const float4 r0 = *reinterpret_cast<const float4*>(rr), r1 = *reinterpret_cast<const float4*>(rr + 4);
+        if (p.epi == EPI_RES_GATE) {
+          const float* gp = p.gate + (size_t)(row / p.rows_per_group) * p.gate_stride + nb;
+          const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
+          o[0] = r0.x + g0.x * o[0]; o[1] = r0.y + g0.y * o[1]; o[2] = r0.z + g0.z * o[2]; o[3] = r0.w + g0.w * o[3];
+          o[4] = r1.x + g1.x * o[4]; o[5] = r1.y + g1.y * o[5]; o[6] = r1.z + g1.z * o[6]; o[7] = r1.w + g1.w * o[7];
+        } else {
+          o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
         }
       }
       if (p.C) {
         float* cr = p.C + (size_t)row * p.ldc + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        *reinterpret_cast<float4*>(cr) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(cr + 4) = make_float4(o[4], o[5], o[6], o[7]);
       }
       if (p.C16) {
+        __align__(16) __nv_bfloat16 hi[8];
+        __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) split_bf16(o[t], hi[t], lo[t]);
         __nv_bfloat16* ch = p.C16 + (size_t)row * p.ldc16 + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          __align__(16) __nv_bfloat16 hi[8];
-          __align__(16) __nv_bfloat16 lo[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) split_bf16(o[j + t], hi[t], lo[t]);
-          *reinterpret_cast<uint4*>(ch + j) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(ch + p.lo_off + j) = *reinterpret_cast<const uint4*>(lo);
-        }
+        *reinterpret_cast<uint4*>(ch) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(ch + p.lo_off) = *reinterpret_cast<const uint4*>(lo);
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 0) TC_STAMP(5);
   }
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
@@ -367,7 +416,7 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
   if ((e = enc.get(g.W16, g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
-             g.M, g.N, g.K, g.epi};
+             g.M, g.N, g.K, g.epi, g.trace};
   if (g.passes == 3) {
     if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {
