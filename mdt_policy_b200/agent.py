@@ -30,8 +30,15 @@ class DenoiseAgent:
         self.sigma_data, self.sigma_min, self.sigma_max = sigma_data, sigma_min, sigma_max
         self.sigma_sample_density_type = sigma_sample_density_type
 
-    # mdtv_agent.py:660-678
+    # mdtv_agent.py:660-678 (memoised: the schedule only depends on the sampler knobs, which stay plain attributes)
     def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):
+        key = (n_sampling_steps, noise_schedule_type, self.sigma_min, self.sigma_max, str(self.device))
+        cache = self.__dict__.setdefault("_schedule_cache", {})
+        if key not in cache:
+            cache[key] = self._build_noise_schedule(n_sampling_steps, noise_schedule_type)
+        return cache[key]
+
+    def _build_noise_schedule(self, n_sampling_steps, noise_schedule_type):
         if noise_schedule_type == 'karras':
             return gcs.get_sigmas_karras(n_sampling_steps, self.sigma_min, self.sigma_max, 7, self.device)
         if noise_schedule_type == 'exponential':

@@ -229,11 +229,11 @@ int launch_attn(MdtHandle* h, const float* q, int ldq, const float* k, const flo
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = h->d; a.y16 = y16; a.ld16 = 2 * h->d; a.lo_off = h->d;
   a.B = B; a.H = h->H; a.hd = h->hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
   a.scale = 1.0f / sqrtf((float)h->hd);
-  // shipped shapes run the compile-time specialised kernel (4 heads per CTA); anything else the generic one
+  // shipped shapes run the compile-time specialised kernel (2 heads per CTA); anything else the generic one
   const bool c = causal != 0;
   #define ATT_CASE(HD, TQ, TK, CA)                                                                                  \
-    if (h->hd == HD && Tq == TQ && Tk == TK && c == (CA != 0) && h->H % 4 == 0) {                                   \
-      launch_pdl(attention_fixed_kernel<HD, TQ, TK, CA, 4>, dim3(B, h->H / 4), dim3(128), 0, st, a);                \
+    if (h->hd == HD && Tq == TQ && Tk == TK && c == (CA != 0) && h->H % 2 == 0) {                                   \
+      launch_pdl(attention_fixed_kernel<HD, TQ, TK, CA, 2>, dim3(B, h->H / 2), dim3(128), 0, st, a);                \
       count_launch(h);                                                                                              \
       return check_launch(h, "attention_fixed_kernel");                                                             \
     }
@@ -916,12 +916,12 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
     std::vector<unsigned long long> tr((size_t)n_cta * 8);
     cudaMemcpy(tr.data(), trace, tr.size() * 8, cudaMemcpyDeviceToHost);
     unsigned long long t0 = ~0ull, t6 = 0;
-    for (int c = 0; c < n_cta; ++c) if (tr[c * 8]) { if (tr[c * 8] < t0) t0 = tr[c * 8]; if (tr[c * 8 + 6] > t6) t6 = tr[c * 8 + 6]; }
-    fprintf(stderr, "[trace] M=%d N=%d K=%d epi=%d: grid span %.2f us; per-CTA ns since first CTA start: entry/setup/first-full/last-full/mma-done/epi-done/exit\n", M, N, K, epi, (t6 - t0) / 1e3);
+    for (int c = 0; c < n_cta; ++c) if (tr[c * 8]) { if (tr[c * 8] < t0) t0 = tr[c * 8]; if (tr[c * 8 + 7] > t6) t6 = tr[c * 8 + 7]; }
+    fprintf(stderr, "[trace] M=%d N=%d K=%d epi=%d: grid span %.2f us; per-CTA ns since first CTA start: entry/setup/first-full/last-full/acc-ready/phaseA-done/sync-done/phaseB-done\n", M, N, K, epi, (t6 - t0) / 1e3);
     for (int c = 0; c < n_cta; c += (n_cta > 6 ? n_cta / 6 : 1)) {
       if (!tr[c * 8]) continue;
       fprintf(stderr, "[trace]   cta %4d:", c);
-      for (int j = 0; j < 7; ++j) fprintf(stderr, " %7lld", (long long)(tr[c * 8 + j] - t0));
+      for (int j = 0; j < 8; ++j) fprintf(stderr, " %7lld", (long long)(tr[c * 8 + j] - t0));
       fprintf(stderr, "\n");
     }
   }

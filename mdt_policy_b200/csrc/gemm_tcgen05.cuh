@@ -250,10 +250,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // warp w may only touch TMEM lanes [32 (w % 4), +32): the four warps of a lane quarter split the BN columns.
     const int q = warp & 3, grp = warp >> 2;
     constexpr int CPW = BN / (THREADS / 128);            // columns per warp: 32 (BN = 128) or 16 (BN = 64)
+    constexpr int GPR = BN / 8;                            // 8-column groups per row (phase B work items)
+    constexpr int ITEMS = BM * GPR / THREADS;              // phase-B items per thread: 2 (BN = 64) or 4 (BN = 128)
+    // residual / gate operands of phase B are fetched now, while the mainloop is still running (this hides their L2
+    // latency, ~1 us); only the BN = 64 instantiation does it, the N >= 1024 GEMMs have no residual epilogue
+    float4 pre_r[BN == 64 ? ITEMS * 2 : 1], pre_g[BN == 64 ? ITEMS * 2 : 1];
+    const bool prefetched = BN == 64 && (p.epi == EPI_RES || p.epi == EPI_RES_GATE) && warp >= 2;
+    if (BN == 64 && prefetched) {
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int idx = threadIdx.x + it * THREADS;
+        const int r = idx / GPR, cg = (idx % GPR) * 8, row = m0 + r;
+        if (row < p.M) {
+          const float* rr = p.R + (size_t)row * p.ldr + n0 + cg;
+          pre_r[it * 2] = *reinterpret_cast<const float4*>(rr); pre_r[it * 2 + 1] = *reinterpret_cast<const float4*>(rr + 4);
+          if (p.epi == EPI_RES_GATE) {
+            const float* gp = p.gate + (size_t)(row / p.rows_per_group) * p.gate_stride + n0 + cg;
+            pre_g[it * 2] = *reinterpret_cast<const float4*>(gp); pre_g[it * 2 + 1] = *reinterpret_cast<const float4*>(gp + 4);
+          }
+        }
+      }
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     pdl_trigger();    // all MMAs of this CTA are done: the next kernel may start its prologue while we drain TMEM
-    if (threadIdx.x == 0) TC_STAMP(4);
+    if (threadIdx.x == 64) TC_STAMP(4);
     // phase A (thread = accumulator row): TMEM -> +bias -> activation -> fp32 staging tile in the (now idle) pipeline smem
     constexpr int SP = BN + 4;                             // padded row stride (floats) of the staging tile
     float* stage = reinterpret_cast<float*>(smem);
@@ -283,10 +304,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 64) TC_STAMP(5);     // a warp-2 thread: phase A done (did not run the producer / MMA loops)
     __syncthreads();
+    if (threadIdx.x == 64) TC_STAMP(6);
     // phase B (coalesced): consecutive threads own consecutive 8-column groups of a row -> full-line global loads/stores
-    constexpr int GPR = BN / 8;                            // 8-column groups per row
-    for (int idx = threadIdx.x; idx < BM * GPR; idx += THREADS) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int idx = threadIdx.x + it * THREADS;
       const int r = idx / GPR, cg = (idx % GPR) * 8;
       const int row = m0 + r;
       if (row >= p.M) continue;
@@ -298,11 +322,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
       }
       if (p.epi == EPI_RES || p.epi == EPI_RES_GATE) {
-        const float* rr = p.R + (size_t)row * p.ldr + nb;
-        const float4 r0 = *reinterpret_cast<const float4*>(rr), r1 = *reinterpret_cast<const float4*>(rr + 4);
+        float4 r0, r1, g0, g1;
+        if (BN == 64 && prefetched) {
+          r0 = pre_r[(BN == 64 ? it : 0) * 2]; r1 = pre_r[(BN == 64 ? it : 0) * 2 + 1];
+          g0 = pre_g[(BN == 64 ? it : 0) * 2]; g1 = pre_g[(BN == 64 ? it : 0) * 2 + 1];
+        } else {
+          const float* rr = p.R + (size_t)row * p.ldr + nb;
+          r0 = *reinterpret_cast<const float4*>(rr); r1 = *reinterpret_cast<const float4*>(rr + 4);
+          if (p.epi == EPI_RES_GATE) {
+            const float* gp = p.gate + (size_t)(row / p.rows_per_group) * p.gate_stride + nb;
+            g0 = *reinterpret_cast<const float4*>(gp); g1 = *reinterpret_cast<const float4*>(gp + 4);
+          }
+        }
         if (p.epi == EPI_RES_GATE) {
-          const float* gp = p.gate + (size_t)(row / p.rows_per_group) * p.gate_stride + nb;
-          const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
           o[0] = r0.x + g0.x * o[0]; o[1] = r0.y + g0.y * o[1]; o[2] = r0.z + g0.z * o[2]; o[3] = r0.w + g0.w * o[3];
           o[4] = r1.x + g1.x * o[4]; o[5] = r1.y + g1.y * o[5]; o[6] = r1.z + g1.z * o[6]; o[7] = r1.w + g1.w * o[7];
         } else {
@@ -325,10 +357,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     tc_fence_before();
-    if (threadIdx.x == 0) TC_STAMP(5);
+    if (threadIdx.x == 64) TC_STAMP(7);
   }
   __syncthreads();
-  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);

@@ -44,12 +44,12 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // largest non-MMA cost.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = 1.0f / fmaf(0.3275911f, z, 1.0f);
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));     // MUFU.RCP (2 ulp) and ex2.approx: far below the
+  float poly = fmaf(1.061405429f, t, -1.453152027f);              // 2^-17 operand rounding of the bf16x3 GEMM that consumes it
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * expf(-z * z);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }

@@ -155,8 +155,23 @@ class _Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def sync_weights(self, owner: nn.Module, prefix: str = "inner_model."):
-        params = list(owner.named_parameters())
-        key = tuple((p.data_ptr(), p._version) for _, p in params)
+        # The module tree is static, so walk it once and keep (name, owning _parameters dict, leaf) triples; every call
+        # then re-reads the live Parameter objects through the dicts (catches re-assigned Parameters as well as in-place
+        # updates: .to(), load_state_dict, EMA swap, optimizer steps bump data_ptr / _version).
+        slots = self.__dict__.get("_slots")
+        if slots is None:
+            slots = []
+            for mname, mod in owner.named_modules():
+                for leaf in mod._parameters:
+                    if mod._parameters[leaf] is not None:
+                        slots.append(((mname + "." if mname else "") + leaf, mod._parameters, leaf))
+            seen, uniq = set(), []
+            for full, d, leaf in slots:              # shared modules (lang_emb is goal_emb without a modality encoder)
+                if id(d[leaf]) not in seen:
+                    seen.add(id(d[leaf])); uniq.append((full, d, leaf))
+            slots = self._slots = uniq
+        params = [(full, d[leaf]) for full, d, leaf in slots]
+        key = tuple([(p.data_ptr(), p._version) for _, p in params])
         if key == self.weights_key:
             return
         for name, p in params:
