@@ -261,6 +261,24 @@ def main():
                      "kernel": "whole sampling graph (encode + 10 steps), algorithmic FLOPs ALG(B,N) of SURVEY 8d",
                      "alg_gflop_per_launch": flops / 1e9, "peak_source": peak_src},
     }
+    # dominant kernel (tcgen05 GEMM, 69 % of kernel time): live CUDA-event timing of back-to-back launches per decoder shape
+    if args.precision != "fp32":
+        try:
+            eng = list(model.inner_model._engines.values())[0]
+            M, d = B * 10, 384
+            shapes = {"qkv (N=3d,K=d)": (M, 3 * d, d, 0), "attn/cross c_proj, cross q (N=d,K=d, +res)": (M, d, d, 4),
+                      "mlp c_fc + GELU (N=4d,K=d)": (M, 4 * d, d, 1), "mlp c_proj + gate + res (N=d,K=4d)": (M, d, 4 * d, 5)}
+            per = {}
+            for name, (m, n, k, epi) in shapes.items():
+                us = eng.gemm_time_us(m, n, k, epi, 200)
+                per[name] = {"us": us, "alg_tflops": 2.0 * m * n * k / us / 1e6, "frac": 2.0 * m * n * k / us / 1e6 / peak}
+            dom = per["mlp c_fc + GELU (N=4d,K=d)"]
+            line["roofline"]["dominant_kernel"] = {
+                "name": "tc::tc_gemm_kernel<128,3> (mlp c_fc + GELU, M=%d N=%d K=%d)" % (M, 4 * d, d), "achieved": dom["alg_tflops"],
+                "frac": dom["frac"], "us_per_launch": dom["us"], "alg_gflop_per_launch": 2.0 * M * 4 * d * d / 1e9,
+                "note": "bf16x3 issues 3x the algorithmic FLOPs: ceiling 1/3", "all_gemm_shapes": per}
+        except Exception as e:  # noqa: BLE001
+            line["roofline"]["dominant_kernel"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         _, desc, _ = cpu_reference_run(enc, dec, B, steps=5, warmup=2, budget_s=40.0)
         line["cpu_baseline"] = desc

@@ -146,6 +146,10 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
                                    const float* gate, int M, int N, int K, int epi, int rows_per_group, float* out,
                                    void* stream);
 
+/* tests / bench only: average duration (us) of `iters` back-to-back launches of the tensor-core GEMM kernel on zero
+ * operands of the given shape (L2-warm), measured with CUDA events on `stream`. */
+MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int epi, int iters, float* avg_us, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

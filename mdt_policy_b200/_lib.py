@@ -20,7 +20,7 @@ EXPORTS = [
     "mdtb200_abi_version", "mdtb200_create", "mdtb200_destroy", "mdtb200_last_error",
     "mdtb200_bind_weight", "mdtb200_commit_weights", "mdtb200_encode", "mdtb200_set_context",
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
-    "mdtb200_debug_copy", "mdtb200_debug_gemm",
+    "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time",
 ]
 
 
@@ -67,6 +67,8 @@ def _declare(lib):
     lib.mdtb200_debug_copy.restype = i64
     lib.mdtb200_debug_gemm.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, fp, vp]
     lib.mdtb200_debug_gemm.restype = i32
+    lib.mdtb200_debug_gemm_time.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_float), vp]
+    lib.mdtb200_debug_gemm_time.restype = i32
     return lib
 
 

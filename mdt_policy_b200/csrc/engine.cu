@@ -40,6 +40,7 @@ struct DecLayerW {
 struct Weights {
   const float *goal0_w, *goal0_b, *goal2_w, *goal2_b;
   const float *lang0_w, *lang0_b, *lang2_w, *lang2_b;
+  const __nv_bfloat16 *goal0_w16, *goal2_w16, *lang0_w16, *lang2_w16, *tok_w16, *incam_w16;
   const float *tok_w, *tok_b, *incam_w, *incam_b, *pos_emb;
   std::vector<EncLayerW> enc;
   std::vector<DecLayerW> dec;
@@ -164,6 +165,13 @@ struct Gemm {
 };
 
 int launch_sgemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
+  if (p.M <= SKINNY_MAXM && p.gi == 0 && !p.C16 && p.epi <= EPI_SILU && p.lda == p.K && p.ldc == p.N && p.K % 4 == 0 &&
+      (size_t)p.M * p.K * 4 <= 48 * 1024) {
+    SkinnyArgs g{p.A, p.W, p.bias, p.C, p.M, p.N, p.K, p.epi};
+    launch_pdl(skinny_gemm_kernel, dim3((p.N + 7) / 8), dim3(256), (size_t)p.M * p.K * 4, st, g);
+    count_launch(h);
+    return check_launch(h, "skinny_gemm_kernel");
+  }
   if (p.K % SG_BK != 0 || p.N % 4 != 0 || p.lda % 4 != 0) return fail(h, MDTB200_EINVAL, "sgemm: unsupported shape M=%d N=%d K=%d", p.M, p.N, p.K);
   GemmArgs g{};
   g.A = p.A; g.lda = p.lda; g.W = p.W; g.bias = p.bias; g.C = p.C; g.ldc = p.ldc; g.R = p.R; g.ldr = p.ldr;
@@ -187,14 +195,14 @@ int launch_sgemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
 // GEMM dispatcher: tensor cores when the handle's precision asks for them and the operand is available in
 // split-bf16 form, exact fp32 CUDA cores otherwise (tiny GEMMs of the sigma path always stay fp32).
 int gemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
-  if (h->cfg.precision != MDTB200_PREC_FP32 && p.A16 && p.W16 && p.gi == 0) {
+  if (h->cfg.precision != MDTB200_PREC_FP32 && p.A16 && p.W16) {
     tc::TcGemm t{};
     t.A16 = p.A16; t.lda16 = p.lda16; t.W16 = p.W16; t.bias = p.bias;
     t.C = p.C; t.ldc = p.ldc; t.C16 = p.C16; t.ldc16 = p.ldc16; t.lo_off = p.lo_off;
     t.R = p.R; t.ldr = p.ldr; t.gate = p.gate; t.gate_stride = p.gate_stride; t.rows_per_group = p.rows_per_group;
     t.M = p.M; t.N = p.N; t.K = p.K; t.epi = p.epi;
     t.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1;
-    t.trace = nullptr;
+    t.trace = nullptr; t.gi = p.gi; t.go = p.go; t.goff = p.goff;
     const char* e = tc::launch_tc_gemm(h->tma, t, st);
     if (e) return fail(h, MDTB200_ECUDA, "tcgen05 gemm (M=%d N=%d K=%d): %s", p.M, p.N, p.K, e);
     count_launch(h);
@@ -287,26 +295,46 @@ int encoder(MdtHandle* h, const Work& k, const float* goal, const float* state, 
   const int d = h->d, Tc = h->Tc, Ts = h->Ts, Mc = B * Tc;
   const Weights& w = h->w;
   const bool lang = modality == MDTB200_MODALITY_LANG && w.lang0_w != nullptr;
+  const bool tcp = use_tc(h);
+  const int G = h->cfg.goal_dim, O = h->cfg.obs_dim;
+  // split-bf16 staging of the embedding inputs inside the (idle) h16 buffer: goal | state | goal-MLP hidden
+  __nv_bfloat16* g16 = k.h16;
+  __nv_bfloat16* s16 = tcp ? k.h16 + (size_t)B * 2 * G : nullptr;
+  __nv_bfloat16* gh16 = tcp ? s16 + (size_t)B * Ts * 2 * O : nullptr;
+  if (tcp) {
+    if ((size_t)B * (2 * G + Ts * 2 * O + 4 * d) > (size_t)B * h->T * 8 * d) return fail(h, MDTB200_EUNSUPPORTED, "embedding staging does not fit");
+    int64_t n = (int64_t)B * G;
+    launch_pdl(split_weights_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, goal, g16, (int64_t)B, G);
+    count_launch(h);
+    n = (int64_t)B * Ts * O;
+    launch_pdl(split_weights_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, state, s16, (int64_t)B * Ts, O);
+    count_launch(h);
+    TRY(check_launch(h, "split_weights_kernel"));
+  }
   {  // goal MLP: Linear(goal_dim, 2d) -> GELU -> Linear(2d, d), written to context token 0
     Gemm g;
-    g.A = goal; g.lda = h->cfg.goal_dim; g.W = lang ? w.lang0_w : w.goal0_w; g.bias = lang ? w.lang0_b : w.goal0_b;
-    g.C = k.gh; g.ldc = 2 * d; g.M = B; g.N = 2 * d; g.K = h->cfg.goal_dim; g.epi = EPI_GELU;
+    g.A = goal; g.lda = G; g.W = lang ? w.lang0_w : w.goal0_w; g.bias = lang ? w.lang0_b : w.goal0_b;
+    g.C = tcp ? nullptr : k.gh; g.ldc = 2 * d; g.M = B; g.N = 2 * d; g.K = G; g.epi = EPI_GELU;
+    if (tcp) { g.A16 = g16; g.lda16 = 2 * G; g.W16 = lang ? w.lang0_w16 : w.goal0_w16; g.C16 = gh16; g.ldc16 = 4 * d; g.lo_off = 2 * d; }
     TRY(gemm(h, g, st));
     Gemm g2;
     g2.A = k.gh; g2.lda = 2 * d; g2.W = lang ? w.lang2_w : w.goal2_w; g2.bias = lang ? w.lang2_b : w.goal2_b;
     g2.C = k.xe; g2.ldc = d; g2.M = B; g2.N = d; g2.K = 2 * d; g2.gi = 1; g2.go = Tc; g2.goff = 0;
+    if (tcp) { g2.A16 = gh16; g2.lda16 = 4 * d; g2.W16 = lang ? w.lang2_w16 : w.goal2_w16; }
     TRY(gemm(h, g2, st));
   }
   if (h->cfg.variant == MDTB200_VARIANT_MDTV) {  // tok_emb on the n_state_tokens Voltron tokens -> context tokens 1..
     Gemm g;
-    g.A = state; g.lda = h->cfg.obs_dim; g.W = w.tok_w; g.bias = w.tok_b; g.C = k.xe; g.ldc = d;
-    g.M = B * Ts; g.N = d; g.K = h->cfg.obs_dim; g.gi = Ts; g.go = Tc; g.goff = 1;
+    g.A = state; g.lda = O; g.W = w.tok_w; g.bias = w.tok_b; g.C = k.xe; g.ldc = d;
+    g.M = B * Ts; g.N = d; g.K = O; g.gi = Ts; g.go = Tc; g.goff = 1;
+    if (tcp) { g.A16 = s16; g.lda16 = 2 * O; g.W16 = w.tok_w16; }
     TRY(gemm(h, g, st));
   } else {  // MDT: token 1 = tok_emb(static), token 2 = incam_embed(gripper); then learned pos_emb
     for (int t = 0; t < 2; ++t) {
       Gemm g;
-      g.A = state + (size_t)t * h->cfg.obs_dim; g.lda = 2 * h->cfg.obs_dim; g.W = t == 0 ? w.tok_w : w.incam_w; g.bias = t == 0 ? w.tok_b : w.incam_b;
-      g.C = k.xe; g.ldc = d; g.M = B; g.N = d; g.K = h->cfg.obs_dim; g.gi = 1; g.go = Tc; g.goff = 1 + t;
+      g.A = state + (size_t)t * O; g.lda = 2 * O; g.W = t == 0 ? w.tok_w : w.incam_w; g.bias = t == 0 ? w.tok_b : w.incam_b;
+      g.C = k.xe; g.ldc = d; g.M = B; g.N = d; g.K = O; g.gi = 1; g.go = Tc; g.goff = 1 + t;
+      if (tcp) { g.A16 = s16 + (size_t)t * 2 * O; g.lda16 = 4 * O; g.W16 = t == 0 ? w.tok_w16 : w.incam_w16; }
       TRY(gemm(h, g, st));
     }
     int n = Mc * d;
@@ -314,7 +342,6 @@ int encoder(MdtHandle* h, const Work& k, const float* goal, const float* state, 
     count_launch(h);
     TRY(check_launch(h, "add_pos_emb_kernel"));
   }
-  const bool tcp = use_tc(h);
   for (int l = 0; l < h->Le; ++l) {  // Block.forward, transformer_blocks.py:209-214
     const EncLayerW& L = w.enc[l];
     TRY(launch_ln(h, k.xe, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln1_w, L.ln1_b, nullptr, nullptr, 0, Mc, st));
@@ -556,8 +583,12 @@ int pack_weights(MdtHandle* h, cudaStream_t st) {
     w.lang0_b = pk.copy("lang_emb.0.bias", 2 * d); w.lang2_w = pk.copy("lang_emb.2.weight", d * 2 * d); w.lang2_b = pk.copy("lang_emb.2.bias", d);
   }
   w.tok_w = pk.copy("tok_emb.weight", d * O); w.tok_b = pk.copy("tok_emb.bias", d);
+  w.goal0_w16 = pk.split(w.goal0_w, 2 * d, (int)G); w.goal2_w16 = pk.split(w.goal2_w, d, (int)(2 * d));
+  if (w.lang0_w) { w.lang0_w16 = pk.split(w.lang0_w, 2 * d, (int)G); w.lang2_w16 = pk.split(w.lang2_w, d, (int)(2 * d)); }
+  w.tok_w16 = pk.split(w.tok_w, d, (int)O);
   if (h->cfg.variant == MDTB200_VARIANT_MDT) {
     w.incam_w = pk.copy("incam_embed.weight", d * O); w.incam_b = pk.copy("incam_embed.bias", d);
+    w.incam_w16 = pk.split(w.incam_w, d, (int)O);
     // pos_emb (1, goal_seq_len + action_seq_len, d): rows 0 and 1 are used by the encoder
     auto it = h->bound.find("inner_model.pos_emb");
     if (it == h->bound.end() || it->second.numel < 2 * d) return fail(h, MDTB200_ESTATE, "weight 'inner_model.pos_emb' missing or too small");
@@ -686,7 +717,7 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   h->arena_floats = arena_size(h);
   if ((rc = dev_alloc(h, &h->arena, h->arena_floats))) return bail(rc);
   if (cfg->precision != MDTB200_PREC_FP32) {
-    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 16 * Dd * Dd) + (1 << 16);
+    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 16 * Dd * Dd + 2 * (2 * Dd * cfg->goal_dim + 2 * Dd * Dd) + 2 * Dd * cfg->obs_dim) + (1 << 16);
     if ((rc = dev_alloc(h, &h->arena16, h->arena16_elems))) return bail(rc);
   }
   h->mod_rows = (int)(B > (size_t)MAX_STEPS ? B : (size_t)MAX_STEPS);
@@ -934,6 +965,41 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
   cudaFree(a16); cudaFree(w16); cudaFree(c16);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "debug_gemm: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Times `iters` back-to-back launches of the tensor-core GEMM kernel (zero operands, pre-split, L2-warm) with CUDA
+// events on `stream`; used by bench.py for the per-kernel roofline entry.  epi as in mdtb200_debug_gemm.
+MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int epi, int iters, float* avg_us, void* stream) {
+  if (!h || !avg_us || iters < 1) return MDTB200_EINVAL;
+  if (h->cfg.precision == MDTB200_PREC_FP32) return fail(h, MDTB200_ESTATE, "debug_gemm_time needs a tensor-core precision handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Mp = (size_t)(M + 127) / 128 * 128;
+  __nv_bfloat16 *a16 = nullptr, *w16 = nullptr, *c16 = nullptr; float *c = nullptr, *gate = nullptr;
+  CUDA_TRY(h, cudaMalloc(&a16, Mp * 2 * K * 2)); CUDA_TRY(h, cudaMalloc(&w16, (size_t)N * 2 * K * 2));
+  CUDA_TRY(h, cudaMalloc(&c16, Mp * 2 * N * 2)); CUDA_TRY(h, cudaMalloc(&c, Mp * N * 4)); CUDA_TRY(h, cudaMalloc(&gate, Mp * N * 4));
+  cudaMemsetAsync(a16, 0, Mp * 2 * K * 2, st); cudaMemsetAsync(w16, 0, (size_t)N * 2 * K * 2, st);
+  cudaMemsetAsync(c, 0, Mp * N * 4, st); cudaMemsetAsync(gate, 0, Mp * N * 4, st);
+  tc::TcGemm t{};
+  t.A16 = a16; t.lda16 = 2 * K; t.W16 = w16; t.C = (epi == EPI_GELU) ? nullptr : c; t.ldc = N;
+  t.C16 = (epi == EPI_GELU) ? c16 : nullptr; t.ldc16 = 2 * N; t.lo_off = N;
+  t.R = c; t.ldr = N; t.gate = gate; t.gate_stride = 0; t.rows_per_group = 10;
+  t.M = M; t.N = N; t.K = K; t.epi = epi; t.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1; t.trace = nullptr;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const char* em = nullptr;
+  for (int i = 0; i < 5 && !em; ++i) em = tc::launch_tc_gemm(h->tma, t, st);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters && !em; ++i) em = tc::launch_tc_gemm(h->tma, t, st);
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  *avg_us = ms * 1000.f / iters;
+  h->launches += iters + 5;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->tma.cache.clear();
+  cudaFree(a16); cudaFree(w16); cudaFree(c16); cudaFree(c); cudaFree(gate);
+  if (em) return fail(h, MDTB200_ECUDA, "debug_gemm_time: %s", em);
+  if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "debug_gemm_time: %s", cudaGetErrorString(e));
   return 0;
 }
 

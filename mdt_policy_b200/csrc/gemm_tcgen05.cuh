@@ -34,6 +34,7 @@ struct TcGemm {
   const float* R; int ldr; const float* gate; int gate_stride; int rows_per_group;
   int M, N, K, epi, passes;
   unsigned long long* trace;
+  int gi, go, goff;            // output-row remap (row = (m / gi) * go + goff + m % gi; gi == 0: identity), C / C16 only
 };
 
 struct TcParams {
@@ -42,6 +43,7 @@ struct TcParams {
   const float* R; int ldr; const float* gate; int gate_stride; int rows_per_group;
   int M, N, K, epi;
   unsigned long long* trace;   // optional (tests): per-CTA globaltimer stamps [cta][8]
+  int gi, go, goff;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -341,8 +343,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
         }
       }
+      const int orow = p.gi ? (row / p.gi) * p.go + p.goff + row % p.gi : row;
       if (p.C) {
-        float* cr = p.C + (size_t)row * p.ldc + nb;
+        float* cr = p.C + (size_t)orow * p.ldc + nb;
         *reinterpret_cast<float4*>(cr) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4*>(cr + 4) = make_float4(o[4], o[5], o[6], o[7]);
       }
@@ -351,7 +354,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) split_bf16(o[t], hi[t], lo[t]);
-        __nv_bfloat16* ch = p.C16 + (size_t)row * p.ldc16 + nb;
+        __nv_bfloat16* ch = p.C16 + (size_t)orow * p.ldc16 + nb;
         *reinterpret_cast<uint4*>(ch) = *reinterpret_cast<const uint4*>(hi);
         *reinterpret_cast<uint4*>(ch + p.lo_off) = *reinterpret_cast<const uint4*>(lo);
       }
@@ -447,7 +450,7 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
   if ((e = enc.get(g.W16, g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
-             g.M, g.N, g.K, g.epi, g.trace};
+             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff};
   if (g.passes == 3) {
     if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {

