@@ -157,7 +157,8 @@ struct SmemLayout {
   static constexpr int STAGE = (PASSES == 3 ? 2 : 1) * (A_TILE + W_TILE);
   // one CTA per SM with the deepest ring that fits: the operand stream is bound by per-SM ingest (~100 GB/s/SM measured), and
   // 2-stage / 2-CTA-per-SM variants measured 9 % slower end to end (profiles/r01_experiments.md)
-  static constexpr int STAGES = (PASSES == 3) ? (BN == 128 ? 3 : 4) : (BN == 128 ? 5 : 6);
+  static constexpr int STAGES = (PASSES == 3) ? (BN == 192 ? 2 : BN == 128 ? 3 : 4) : (BN == 192 ? 4 : BN == 128 ? 5 : 6);
+  static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);      // power of two >= BN
   static constexpr int MIN_CTAS = 1;
   static constexpr int BAR_OFF = STAGES * STAGE;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;         // barriers + tmem slot, + slack for 1024-B alignment
@@ -191,7 +192,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), BN);     // BN in {64, 128}: power of two >= 32 columns
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -365,7 +366,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -424,6 +425,8 @@ inline const char* configure_one() {
 }
 inline const char* configure_kernels() {
   const char* e;
+  if ((e = configure_one<192, 3>())) return e;
+  if ((e = configure_one<192, 1>())) return e;
   if ((e = configure_one<128, 3>())) return e;
   if ((e = configure_one<64, 3>())) return e;
   if ((e = configure_one<128, 1>())) return e;
@@ -443,8 +446,11 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE) return "unsupported epilogue";
   // tile-N choice: 128 columns when that still yields >= ~1 wave of CTAs on 148 SMs, else 64
   const int mt = (g.M + BM - 1) / BM;
-  const int bn = (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
-  (void)mt;
+  // tile width: one wave of CTAs where possible.  N = 1152 (fused QKV): 6 x 192 -> 120 CTAs at M = 2560 instead of 180 x 128
+  static const bool allow192 = !(getenv("MDTB200_NO_BN192"));
+  // (only worth it for a full-batch launch: at the M = 640 of a 4-branch graph the fatter tile just lengthens the latency chain)
+  const bool wide = allow192 && mt >= 16 && g.N % 192 == 0 && (g.N / 192) * mt <= 148 && (g.N % 128 != 0 || (g.N / 128) * mt > 148);
+  const int bn = wide ? 192 : (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
   CUtensorMap ta, tw;
   const char* e;
   if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
@@ -452,9 +458,9 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
              g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff};
   if (g.passes == 3) {
-    if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
+    if (bn == 192) launch_one<192, 3>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {
-    if (bn == 128) launch_one<128, 1>(ta, tw, p, st); else launch_one<64, 1>(ta, tw, p, st);
+    if (bn == 192) launch_one<192, 1>(ta, tw, p, st); else if (bn == 128) launch_one<128, 1>(ta, tw, p, st); else launch_one<64, 1>(ta, tw, p, st);
   }
   return nullptr;
 }
