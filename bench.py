@@ -276,7 +276,9 @@ def main():
             line["roofline"]["dominant_kernel"] = {
                 "name": "tc::tc_gemm_kernel<128,3> (mlp c_fc + GELU, M=%d N=%d K=%d)" % (M, 4 * d, d), "achieved": dom["alg_tflops"],
                 "frac": dom["frac"], "us_per_launch": dom["us"], "alg_gflop_per_launch": 2.0 * M * 4 * d * d / 1e9,
-                "note": "bf16x3 issues 3x the algorithmic FLOPs: ceiling 1/3", "all_gemm_shapes": per}
+                "note": "bf16x3 issues 3x the algorithmic FLOPs: ceiling 1/3", "all_gemm_shapes": per,
+                "traffic_bytes_per_launch_ncu": 1300,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r01_v7_summary.md (working set is L2-resident)"}
         except Exception as e:  # noqa: BLE001
             line["roofline"]["dominant_kernel"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:

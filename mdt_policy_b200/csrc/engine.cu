@@ -88,7 +88,7 @@ struct MdtHandle {
   Weights w;
 
   // workspace
-  float *in_goal = nullptr, *in_state = nullptr, *x = nullptr, *x2 = nullptr, *dbuf = nullptr, *sigmas = nullptr, *out = nullptr;
+  float *in_goal = nullptr, *in_state = nullptr, *x = nullptr, *x2 = nullptr, *dbuf = nullptr, *sigmas = nullptr;
   float *gh = nullptr, *xe = nullptr, *ctx = nullptr, *kv = nullptr, *xh = nullptr, *a = nullptr, *qkv = nullptr, *y = nullptr, *hbuf = nullptr, *q = nullptr;
   float *pe = nullptr, *sh = nullptr, *cs = nullptr, *mod = nullptr;
   __nv_bfloat16 *a16 = nullptr, *y16 = nullptr, *h16 = nullptr;   // split-bf16 operand copies (hi | lo)
@@ -723,7 +723,7 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   h->mod_rows = (int)(B > (size_t)MAX_STEPS ? B : (size_t)MAX_STEPS);
   const size_t R = h->mod_rows;
   if ((rc = dev_alloc(h, &h->in_goal, B * cfg->goal_dim)) || (rc = dev_alloc(h, &h->in_state, B * h->Ts * cfg->obs_dim)) ||
-      (rc = dev_alloc(h, &h->x, M * h->A)) || (rc = dev_alloc(h, &h->x2, M * h->A)) || (rc = dev_alloc(h, &h->dbuf, M * h->A)) || (rc = dev_alloc(h, &h->out, M * h->A)) ||
+      (rc = dev_alloc(h, &h->x, M * h->A)) || (rc = dev_alloc(h, &h->x2, M * h->A)) || (rc = dev_alloc(h, &h->dbuf, M * h->A)) ||
       (rc = dev_alloc(h, &h->sigmas, (size_t)MAX_STEPS + 8 + B)) ||
       (rc = dev_alloc(h, &h->gh, B * 2 * Dd)) || (rc = dev_alloc(h, &h->xe, M * Dd)) || (rc = dev_alloc(h, &h->ctx, M * Dd)) ||
       (rc = dev_alloc(h, &h->kv, B * h->Tc * h->Ld * 2 * Dd)) || (rc = dev_alloc(h, &h->xh, M * Dd)) || (rc = dev_alloc(h, &h->a, M * Dd)) ||

@@ -197,6 +197,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The weight tiles do not depend on the previous kernel: the producer requests them for the first ring pass BEFORE the
+  // dependency wait, so that under PDL they stream in while the predecessor is still draining its epilogue.
+  const int npre = nkb < L::STAGES ? nkb : L::STAGES;
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < npre; ++kb) {
+      const uint32_t st = sbase + kb * L::STAGE;
+      mbar_expect_tx(full_bar(kb), L::STAGE);
+      tma_load_2d(st + L::A_TILE, &tmW, full_bar(kb), kb * BK, n0);                                         // W hi
+      if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(kb), p.K + kb * BK, n0);  // W lo
+    }
+  }
   pdl_wait();       // prologue above overlapped the previous kernel's tail; its results are visible from here on
   if (threadIdx.x == 0) TC_STAMP(1);
 
@@ -206,15 +217,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % L::STAGES;
         const uint32_t ph = (kb / L::STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t st = sbase + s * L::STAGE;
-        mbar_expect_tx(full_bar(s), L::STAGE);
-        tma_load_2d(st, &tmA, full_bar(s), kb * BK, m0);                       // A hi
-        tma_load_2d(st + L::A_TILE, &tmW, full_bar(s), kb * BK, n0);           // W hi
-        if (PASSES == 3) {
-          tma_load_2d(st + L::A_TILE + L::W_TILE, &tmA, full_bar(s), p.K + kb * BK, m0);              // A lo
-          tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(s), p.K + kb * BK, n0);          // W lo
+        if (kb >= npre) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), L::STAGE);
+          tma_load_2d(st + L::A_TILE, &tmW, full_bar(s), kb * BK, n0);                                         // W hi
+          if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(s), p.K + kb * BK, n0);  // W lo
         }
+        tma_load_2d(st, &tmA, full_bar(s), kb * BK, m0);                                                       // A hi
+        if (PASSES == 3) tma_load_2d(st + L::A_TILE + L::W_TILE, &tmA, full_bar(s), p.K + kb * BK, m0);        // A lo
       }
     }
   } else if (warp == 1) {

@@ -122,7 +122,6 @@ class _Engine:
         self.max_batch = int(max_batch)
         self.handle = C.c_void_p()
         self.weights_key = None
-        self.ctx_key = None
         cfg = _lib.MdtConfig(
             abi_version=_lib.ABI_VERSION, variant=_lib.VARIANT[owner._variant], embed_dim=owner.embed_dim,
             n_heads=owner.n_heads, n_enc_layers=owner.n_enc_layers, n_dec_layers=owner.n_dec_layers,
@@ -183,7 +182,6 @@ class _Engine:
             self.check(self.lib.mdtb200_bind_weight(self.handle, (prefix + name).encode(), _ptr(t), t.numel()), "bind_weight")
         self.check(self.lib.mdtb200_commit_weights(self.handle, self.stream), "commit_weights")
         self.weights_key = key
-        self.ctx_key = None
 
     def launch_count(self) -> int:
         return int(self.lib.mdtb200_launch_count(self.handle))
