@@ -240,6 +240,7 @@ def main():
 
     agg = D.aggregate_throughput(args.steps * N_STEPS, t_dev, device=dev)      # the one collective: throughput counters
     agg_e2e = D.aggregate_throughput(args.steps * N_STEPS, t_e2e, device=dev)
+    D.shutdown()
     if rank != 0:
         return 0
 

@@ -51,3 +51,8 @@ def aggregate_throughput(local_units: float, local_seconds: float, device="cpu")
     units, secs = float(allv[:, 0].sum()), float(allv[:, 1].max())
     return {"units": units, "seconds": secs, "throughput": units / secs if secs > 0 else 0.0,
             "per_rank": [(float(u), float(s)) for u, s in allv.tolist()]}
+
+
+def shutdown():
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
