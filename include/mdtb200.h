@@ -140,6 +140,32 @@ MDTB200_API int64_t mdtb200_launch_count(const MdtHandle* h);
  * "y", "h", "q" ... into dst (device, capacity in floats); returns #floats or <0 */
 MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* dst_dev, int64_t capacity, void* stream);
 
+/* training primitives --------------------------------------------------------------------------
+ * Stateless exact-fp32 ops (no handle; errors through mdtb200_last_error(NULL)) from which the Python side builds the
+ * autograd graph of GCDenoiser.loss (score_wrappers.py:45-63): every FLOP of the training forward and backward runs in
+ * these kernels.  All tensors contiguous fp32 on the current device; `stream` as above. */
+/* mode 0: C[M,N] = A[M,K] B[N,K]^T (+bias)   mode 1: C[M,K] = A[M,N] B[N,K]   mode 2: C[N,K] (+)= A[M,N]^T B[M,K] */
+MDTB200_API int mdtb200_op_gemm(int mode, const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                                int accumulate, void* stream);
+MDTB200_API int mdtb200_op_group_sum(const float* src, float* out, int G, int T, int C, int accumulate, void* stream);
+MDTB200_API int mdtb200_op_colsum(const float* src, float* out, float* scratch, int M, int C, int accumulate, void* stream);
+/* dy == NULL: out = act(x); else out = dy * act'(x).  act: 1 GELU(erf), 2 Mish, 3 SiLU */
+MDTB200_API int mdtb200_op_act(const float* x, const float* dy, float* out, int64_t n, int act, void* stream);
+MDTB200_API int mdtb200_op_ln_fwd(const float* x, const float* w, const float* b, const float* shift, const float* scale,
+                                  int mod_stride, int rows_per_group, int M, int d, float* y, void* stream);
+MDTB200_API int mdtb200_op_ln_bwd(const float* x, const float* dy, const float* w, const float* b, const float* scale,
+                                  int mod_stride, int rows_per_group, int M, int d, float* dx, float* t_dw, float* t_db,
+                                  float* t_dsc, void* stream);
+MDTB200_API int mdtb200_op_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* y, int ldy,
+                                    int B, int H, int hd, int Tq, int Tk, int causal, void* stream);
+MDTB200_API int mdtb200_op_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dy, int lddy,
+                                    float* dq, int lddq, float* dk, float* dv, int lddkv, int B, int H, int hd, int Tq, int Tk,
+                                    int causal, void* stream);
+MDTB200_API int mdtb200_op_gate_res(const float* x, const float* f, const float* gate, float* out, int M, int d,
+                                    int rows_per_group, void* stream);
+MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const float* gate, float* df, float* prod, int M, int d,
+                                        int rows_per_group, void* stream);
+
 /* tests only: out (M,N) = epi(A (M,K) . W (N,K)^T + bias) through the tensor-core GEMM kernel on fp32 inputs
  * (epi: 0 none, 1 GELU, 4 residual R (M,N), 5 residual + gate[(m / rows_per_group), n] (gate row stride N)). */
 MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W, const float* bias, const float* R,

@@ -1,0 +1,180 @@
+// Stateless fp32 primitive ops of the TRAINING path, exported through the C ABI (include/mdtb200.h, "training primitives").
+// The Python side (mdt_policy_b200/training.py) composes them into autograd Functions that mirror the reference's
+// train-mode forward (score_wrappers.py:45-63 -> mdtv_transformer.py:208-236); every FLOP of forward and backward runs in
+// these kernels.  Included by engine.cu (single translation unit).
+#pragma once
+#include "kernels_train.cuh"
+
+namespace {
+
+int op_fail(int code, const char* fmt, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_create_error = buf;
+  return code;
+}
+int op_check(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return op_fail(MDTB200_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e)); }
+  return 0;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+// mode 0: C[M,N] = A[M,K] . B[N,K]^T (+ bias[N])     forward of nn.Linear (A = x, B = weight)
+// mode 1: C[M,K] = A[M,N] . B[N,K]                  input gradient      (A = dy, B = weight)
+// mode 2: C[N,K] (+)= A[M,N]^T . B[M,K]             weight gradient     (A = dy, B = x)
+MDTB200_API int mdtb200_op_gemm(int mode, const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                                int accumulate, void* stream) {
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1 || mode < 0 || mode > 2) return op_fail(MDTB200_EINVAL, "op_gemm: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool al = aligned16(A) && aligned16(B) && aligned16(C);
+  if (mode == 0 && al && K % 16 == 0 && N % 4 == 0 && !accumulate && (!bias || aligned16(bias))) {
+    GemmArgs g{};
+    g.A = A; g.lda = K; g.W = B; g.bias = bias; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K; g.rows_per_group = 1;
+    dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
+    sgemm_tn_kernel<EPI_NONE><<<grid, SG_THREADS, 0, st>>>(g);
+    return op_check("sgemm_tn_kernel");
+  }
+  if (mode == 1 && al && N % 16 == 0 && K % 4 == 0 && !bias) {
+    GGemmArgs g{A, N, B, K, C, K, M, K, N, accumulate};
+    dim3 grid((K + 63) / 64, (M + 127) / 128);
+    ggemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
+    return op_check("ggemm_kernel<dgrad>");
+  }
+  if (mode == 2 && al && N % 4 == 0 && K % 4 == 0 && !bias) {
+    GGemmArgs g{A, N, B, K, C, K, N, K, M, accumulate};
+    dim3 grid((K + 63) / 64, (N + 127) / 128);
+    ggemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+    return op_check("ggemm_kernel<wgrad>");
+  }
+  if (accumulate) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm: accumulate needs 4-aligned dims");
+  // tiny / odd dimensions (the 7-wide action embedding and output head): strided naive kernel
+  NaiveArgs n{};
+  n.bias = bias; n.C = C;
+  if (mode == 0) { n.A = A; n.sa_i = K; n.sa_r = 1; n.B = B; n.sb_r = 1; n.sb_j = K; n.I = M; n.J = N; n.R = K; n.sc_i = N; n.sc_j = 1; }
+  if (mode == 1) { n.A = A; n.sa_i = N; n.sa_r = 1; n.B = B; n.sb_r = K; n.sb_j = 1; n.I = M; n.J = K; n.R = N; n.sc_i = K; n.sc_j = 1; }
+  if (mode == 2) { n.A = A; n.sa_i = 1; n.sa_r = N; n.B = B; n.sb_r = K; n.sb_j = 1; n.I = N; n.J = K; n.R = M; n.sc_i = K; n.sc_j = 1; }
+  const long tot = (long)n.I * n.J;
+  naive_gemm_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(n);
+  return op_check("naive_gemm_kernel");
+}
+
+// out[g, c] (+)= sum_t src[g*T + t, c]
+MDTB200_API int mdtb200_op_group_sum(const float* src, float* out, int G, int T, int Cn, int accumulate, void* stream) {
+  if (!src || !out || G < 1 || T < 1 || Cn < 1) return op_fail(MDTB200_EINVAL, "op_group_sum: bad argument");
+  const long tot = (long)G * Cn;
+  group_sum_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src, out, G, T, Cn, accumulate);
+  return op_check("group_sum_kernel");
+}
+
+// column sum of a tall matrix in two deterministic stages; `scratch` holds ceil(M / 64) * C floats
+MDTB200_API int mdtb200_op_colsum(const float* src, float* out, float* scratch, int M, int Cn, int accumulate, void* stream) {
+  if (!src || !out || !scratch || M < 1 || Cn < 1) return op_fail(MDTB200_EINVAL, "op_colsum: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int slabs = (M + 63) / 64;
+  colsum_partial_kernel<<<dim3((Cn + 127) / 128, slabs), 128, 0, st>>>(src, scratch, M, Cn, 64);
+  const long tot = Cn;
+  group_sum_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(scratch, out, 1, slabs, Cn, accumulate);
+  return op_check("colsum kernels");
+}
+
+// dy == NULL: out = act(x) ; else out = dy * act'(x).   act: 1 GELU(erf), 2 Mish, 3 SiLU
+MDTB200_API int mdtb200_op_act(const float* x, const float* dy, float* out, int64_t n, int act, void* stream) {
+  if (!x || !out || n < 1 || act < ACT_GELU || act > ACT_SILU) return op_fail(MDTB200_EINVAL, "op_act: bad argument");
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dy) act_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, dy, out, (long)n, act);
+  else act_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, (long)n, act);
+  return op_check("act kernel");
+}
+
+// y = shift + LN(x; w, b) * scale   (shift/scale NULL: plain LayerNorm); shift/scale rows = (row / rows_per_group) * mod_stride
+MDTB200_API int mdtb200_op_ln_fwd(const float* x, const float* w, const float* b, const float* shift, const float* scale, int mod_stride,
+                                  int rows_per_group, int M, int d, float* y, void* stream) {
+  if (!x || !w || !y || M < 1 || d % 128 != 0 || d > 1024 || rows_per_group < 1) return op_fail(MDTB200_EINVAL, "op_ln_fwd: bad argument");
+  LnArgs a{};
+  a.x = x; a.out = y; a.w = w; a.b = b; a.shift = shift; a.scale = scale; a.mod_stride = mod_stride; a.rows_per_group = rows_per_group; a.M = M; a.d = d;
+  const int blocks = (M * 32 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d / 128) {
+    case 1: ln_mod_kernel<1><<<blocks, 256, 0, st>>>(a); break;
+    case 2: ln_mod_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    case 3: ln_mod_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+    case 4: ln_mod_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 6: ln_mod_kernel<6><<<blocks, 256, 0, st>>>(a); break;
+    case 8: ln_mod_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    default: return op_fail(MDTB200_EUNSUPPORTED, "op_ln_fwd: d = %d", d);
+  }
+  return op_check("ln_mod_kernel");
+}
+
+// backward of the op above: dx, and the per-row terms whose column / group sums are the parameter gradients:
+//   t_dw = dn * xhat (-> d ln.weight), t_db = dn (-> d ln.bias), t_dsc = dy * n (-> d scale, group sum); d shift = group sum of dy
+MDTB200_API int mdtb200_op_ln_bwd(const float* x, const float* dy, const float* w, const float* b, const float* scale, int mod_stride,
+                                  int rows_per_group, int M, int d, float* dx, float* t_dw, float* t_db, float* t_dsc, void* stream) {
+  if (!x || !dy || !w || !dx || M < 1 || d % 128 != 0 || d > 1024 || rows_per_group < 1) return op_fail(MDTB200_EINVAL, "op_ln_bwd: bad argument");
+  LnBwdArgs a{x, dy, w, b, scale, mod_stride, rows_per_group, dx, t_dw, t_db, t_dsc, M, d};
+  const int blocks = (M * 32 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d / 128) {
+    case 1: ln_bwd_kernel<1><<<blocks, 256, 0, st>>>(a); break;
+    case 2: ln_bwd_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    case 3: ln_bwd_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+    case 4: ln_bwd_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 6: ln_bwd_kernel<6><<<blocks, 256, 0, st>>>(a); break;
+    case 8: ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    default: return op_fail(MDTB200_EUNSUPPORTED, "op_ln_bwd: d = %d", d);
+  }
+  return op_check("ln_bwd_kernel");
+}
+
+// softmax(q k^T / sqrt(hd) + causal-top-left mask) v for T <= 16; strided operands (row stride in floats)
+MDTB200_API int mdtb200_op_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* y, int ldy, int B, int H, int hd,
+                                    int Tq, int Tk, int causal, void* stream) {
+  if (!q || !k || !v || !y || B < 1 || H < 1 || hd < 4 || hd % 4 || hd > ATT_MAXHD || Tq < 1 || Tq > ATT_MAXT || Tk < 1 || Tk > ATT_MAXT)
+    return op_fail(MDTB200_EINVAL, "op_attn_fwd: bad argument");
+  AttnArgs a{};
+  a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = ldy; a.B = B; a.H = H; a.hd = hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
+  a.scale = 1.0f / sqrtf((float)hd);
+  const size_t smem = attention_smem_bytes(H * hd, H, Tq, Tk);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return op_fail(MDTB200_ECUDA, "attention smem %zu", smem);
+    configured = smem;
+  }
+  attention_kernel<<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>(a);
+  return op_check("attention_kernel");
+}
+
+MDTB200_API int mdtb200_op_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dy, int lddy, float* dq,
+                                    int lddq, float* dk, float* dv, int lddkv, int B, int H, int hd, int Tq, int Tk, int causal, void* stream) {
+  if (!q || !k || !v || !dy || !dq || !dk || !dv || B < 1 || H < 1 || hd < 1 || hd > ATT_MAXHD || Tq < 1 || Tq > ATT_MAXT || Tk < 1 || Tk > ATT_MAXT)
+    return op_fail(MDTB200_EINVAL, "op_attn_bwd: bad argument");
+  AttnBwdArgs a{q, ldq, k, v, ldkv, dy, lddy, dq, lddq, dk, dv, lddkv, B, H, hd, Tq, Tk, causal, 1.0f / sqrtf((float)hd)};
+  attention_bwd_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(a);
+  return op_check("attention_bwd_kernel");
+}
+
+// out = x + gate[row / rows_per_group] * f   (gate NULL: out = x + f)
+MDTB200_API int mdtb200_op_gate_res(const float* x, const float* f, const float* gate, float* out, int M, int d, int rows_per_group, void* stream) {
+  if (!x || !f || !out || M < 1 || d < 1 || rows_per_group < 1) return op_fail(MDTB200_EINVAL, "op_gate_res: bad argument");
+  const long n = (long)M * d;
+  gate_res_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, f, gate, out, M, d, rows_per_group);
+  return op_check("gate_res_fwd_kernel");
+}
+// df = gate * dout ; prod = dout * f (group-sum it for d gate; may be NULL)
+MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const float* gate, float* df, float* prod, int M, int d,
+                                        int rows_per_group, void* stream) {
+  if (!dout || !f || !df || M < 1 || d < 1 || rows_per_group < 1) return op_fail(MDTB200_EINVAL, "op_gate_res_bwd: bad argument");
+  const long n = (long)M * d;
+  gate_res_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, f, gate, df, prod, M, d, rows_per_group);
+  return op_check("gate_res_bwd_kernel");
+}
+
+}  // extern "C"

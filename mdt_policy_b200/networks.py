@@ -309,11 +309,29 @@ class _ScoreNetBase(nn.Module):
                       "mdtb200_denoise")
         return out
 
+    def wants_grad(self, *tensors) -> bool:
+        """True when autograd must see this call: gradients enabled and a parameter (or an input) requires them."""
+        if not torch.is_grad_enabled():
+            return False
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())
+
     def forward(self, states, actions, goals, sigma, uncond: Optional[bool] = False, _precondition: bool = False):
+        if self.wants_grad(actions, goals):
+            # training path: exact-fp32 CUDA kernels with hand-written backward, composed under torch.autograd (training.py)
+            from . import training
+            if _precondition:
+                raise RuntimeError("internal: the fused preconditioner has no backward; GCDenoiser applies the scalings itself")
+            if uncond:
+                goals = torch.zeros_like(goals)
+            return training.forward_train(self, states, actions, goals, sigma)
         eng, _ = self._encode(states, goals, uncond, context_only=False)
         return self._decode(eng, actions, sigma, _precondition)
 
     def forward_enc_only(self, states, actions=None, goals=None, sigma=None, uncond: Optional[bool] = False):
+        if self.wants_grad(goals) and self._variant == "mdtv":
+            from . import training
+            training._check_no_dropout(self)
+            return training.encode_train(self, states, torch.zeros_like(goals) if uncond else goals)
         _, ctx = self._encode(states, goals, uncond, context_only=True)
         return ctx
 

@@ -48,18 +48,18 @@ class GCDenoiser(nn.Module):
         return sd2 / denom, sigma * self.sigma_data / denom ** 0.5, 1 / denom ** 0.5
 
     def forward(self, state, action, goal, sigma, **kwargs):
-        """score_wrappers.py:65-80: inner(state, action*c_in, goal, sigma) * c_out + action * c_skip,
-        with the three scalings applied inside the CUDA kernels."""
+        """score_wrappers.py:65-80: inner(state, action*c_in, goal, sigma) * c_out + action * c_skip.  Without autograd the
+        three scalings are applied inside the CUDA kernels; with autograd (training path) they are plain tensor ops around
+        the differentiable score network."""
+        if self.inner_model.wants_grad(action, goal):
+            c_skip, c_out, c_in = [append_dims(x, action.ndim) for x in self.get_scalings(sigma)]
+            return self.inner_model(state, action * c_in, goal, sigma, **kwargs) * c_out + action * c_skip
         return self.inner_model(state, action, goal, sigma, _precondition=True, **kwargs)
 
     def loss(self, state, action, goal, noise, sigma, **kwargs):
-        """score_wrappers.py:45-63.  Forward value only: the hand-written backward pass is not part of this
-        round, so calling it with autograd enabled on trainable parameters raises instead of silently
-        returning a loss without a graph."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.inner_model.parameters()):
-            raise NotImplementedError(
-                "GCDenoiser.loss: backward through the CUDA score network is not implemented yet; "
-                "wrap the call in torch.no_grad() to evaluate the loss value")
+        """score_wrappers.py:45-63.  With autograd enabled the score network runs through the training path
+        (mdt_policy_b200/training.py: fp32 CUDA kernels with hand-written backward) and `loss.backward()` fills the
+        parameter gradients; under torch.no_grad() the inference kernels evaluate the same value."""
         c_skip, c_out, c_in = [append_dims(x, action.ndim) for x in self.get_scalings(sigma)]
         noised_input = action + noise * append_dims(sigma, action.ndim)
         model_output = self.inner_model(state, noised_input * c_in, goal, sigma, **kwargs)

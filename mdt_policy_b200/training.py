@@ -1,0 +1,282 @@
+"""Training path: GCDenoiser.loss with gradients (mdt/models/edm_diffusion/score_wrappers.py:45-63 ->
+mdtv_transformer.py:208-236 -> transformer_blocks.py Block / ConditionedBlock / Attention / MLP / LayerNorm).
+
+The graph is held by torch.autograd (plumbing: saved tensors, gradient accumulation over the residual stream and the
+shared sigma embedding), but every node is one of the autograd Functions below whose forward AND backward are the
+exact-fp32 CUDA kernels of libmdtb200.so (C ABI "training primitives": mdtb200_op_*).  Semantics are the reference's
+train-mode forward with all dropout probabilities and goal_drop equal to 0 -- dropout kernels are not implemented yet and
+a model configured with p > 0 raises instead of silently training without it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+ACT_GELU, ACT_MISH, ACT_SILU = 1, 2, 3
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {_lib.load().mdtb200_last_error(None).decode()}")
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError("mdt_policy_b200 training path runs only on CUDA tensors; there is no CPU fallback")
+
+
+def _colsum(src2d):
+    M, Cn = src2d.shape
+    out = torch.empty(Cn, dtype=torch.float32, device=src2d.device)
+    scratch = torch.empty(((M + 63) // 64) * Cn, dtype=torch.float32, device=src2d.device)
+    _chk(_lib.load().mdtb200_op_colsum(_p(src2d), _p(out), _p(scratch), M, Cn, 0, _stream(src2d)), "op_colsum")
+    return out
+
+
+def _group_sum(src2d, G, T):
+    Cn = src2d.shape[1]
+    out = torch.empty(G, Cn, dtype=torch.float32, device=src2d.device)
+    _chk(_lib.load().mdtb200_op_group_sum(_p(src2d), _p(out), G, T, Cn, 0, _stream(src2d)), "op_group_sum")
+    return out
+
+
+class Linear(Function):
+    """y = x W^T + b  (nn.Linear);  dx = dy W, dW = dy^T x, db = colsum(dy)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _require_cuda(x)
+        K, N = w.shape[1], w.shape[0]
+        x2 = _c(x).reshape(-1, K)
+        y = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+        _chk(_lib.load().mdtb200_op_gemm(0, _p(x2), _p(w), _p(b), _p(y), x2.shape[0], N, K, 0, _stream(x)), "op_gemm fwd")
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        lib = _lib.load()
+        N, K = w.shape
+        M = x2.shape[0]
+        dy2 = _c(dy).reshape(M, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+            _chk(lib.mdtb200_op_gemm(1, _p(dy2), _p(w), None, _p(dx), M, N, K, 0, _stream(dy)), "op_gemm dgrad")
+            dx = dx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+            _chk(lib.mdtb200_op_gemm(2, _p(dy2), _p(x2), None, _p(dw), M, N, K, 0, _stream(dy)), "op_gemm wgrad")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(dy2)
+        return dx, dw, db
+
+
+class Act(Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        _require_cuda(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        _chk(_lib.load().mdtb200_op_act(_p(x), None, _p(y), x.numel(), kind, _stream(x)), "op_act fwd")
+        ctx.save_for_backward(x)
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        _chk(_lib.load().mdtb200_op_act(_p(x), _p(dy), _p(dx), x.numel(), ctx.kind, _stream(x)), "op_act bwd")
+        return dx, None
+
+
+class LayerNormMod(Function):
+    """y = shift + LN(x; w, b) * scale (shift/scale (B, d) per sample, or None for a plain LayerNorm)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, shift, scale):
+        _require_cuda(x)
+        B, T, d = x.shape
+        x = _c(x)
+        shift = _c(shift) if shift is not None else None
+        scale = _c(scale) if scale is not None else None
+        y = torch.empty_like(x)
+        _chk(_lib.load().mdtb200_op_ln_fwd(_p(x), _p(w), _p(b), _p(shift), _p(scale), d, T, B * T, d, _p(y), _stream(x)), "op_ln_fwd")
+        ctx.save_for_backward(x, w, b, scale)
+        ctx.mod = shift is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, scale = ctx.saved_tensors
+        B, T, d = x.shape
+        M = B * T
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        t_dw = torch.empty(M, d, dtype=torch.float32, device=x.device)
+        t_db = torch.empty(M, d, dtype=torch.float32, device=x.device) if b is not None else None
+        t_dsc = torch.empty(M, d, dtype=torch.float32, device=x.device) if ctx.mod else None
+        _chk(_lib.load().mdtb200_op_ln_bwd(_p(x), _p(dy), _p(w), _p(b), _p(scale), d, T, M, d, _p(dx), _p(t_dw), _p(t_db), _p(t_dsc),
+                                           _stream(x)), "op_ln_bwd")
+        dw = _colsum(t_dw)
+        db = _colsum(t_db) if b is not None else None
+        dshift = _group_sum(dy.view(M, d), B, T) if ctx.mod else None
+        dscale = _group_sum(t_dsc, B, T) if ctx.mod else None
+        return dx, dw, db, dshift, dscale
+
+
+class Attention(Function):
+    """softmax(q k^T / sqrt(hd) + mask) v over heads; q (B,Tq,D), k/v (B,Tk,D)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, n_heads, causal):
+        _require_cuda(q)
+        q, k, v = _c(q), _c(k), _c(v)
+        B, Tq, D = q.shape
+        Tk = k.shape[1]
+        y = torch.empty_like(q)
+        _chk(_lib.load().mdtb200_op_attn_fwd(_p(q), D, _p(k), _p(v), D, _p(y), D, B, n_heads, D // n_heads, Tq, Tk, int(causal),
+                                             _stream(q)), "op_attn_fwd")
+        ctx.save_for_backward(q, k, v)
+        ctx.cfg = (n_heads, int(causal))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        q, k, v = ctx.saved_tensors
+        H, causal = ctx.cfg
+        B, Tq, D = q.shape
+        Tk = k.shape[1]
+        dy = _c(dy)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _chk(_lib.load().mdtb200_op_attn_bwd(_p(q), D, _p(k), _p(v), D, _p(dy), D, _p(dq), D, _p(dk), _p(dv), D, B, H, D // H, Tq, Tk,
+                                             causal, _stream(q)), "op_attn_bwd")
+        return dq, dk, dv, None, None
+
+
+class GateResidual(Function):
+    """out = x + gate * f  (gate (B, d) broadcast over tokens, or None: out = x + f)."""
+
+    @staticmethod
+    def forward(ctx, x, f, gate):
+        _require_cuda(x)
+        x, f = _c(x), _c(f)
+        gate = _c(gate) if gate is not None else None
+        B, T, d = x.shape
+        out = torch.empty_like(x)
+        _chk(_lib.load().mdtb200_op_gate_res(_p(x), _p(f), _p(gate), _p(out), B * T, d, T, _stream(x)), "op_gate_res")
+        ctx.save_for_backward(f, gate)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f, gate = ctx.saved_tensors
+        B, T, d = f.shape
+        dout = _c(dout)
+        df = torch.empty_like(f)
+        prod = torch.empty_like(f) if gate is not None else None
+        _chk(_lib.load().mdtb200_op_gate_res_bwd(_p(dout), _p(f), _p(gate), _p(df), _p(prod), B * T, d, T, _stream(f)), "op_gate_res_bwd")
+        dgate = _group_sum(prod.view(B * T, d), B, T) if gate is not None else None
+        return dout, df, dgate
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# train-mode forward of the score network, composed of the Functions above (same structure as the reference modules)
+
+def _lin(mod, x):
+    return Linear.apply(x, mod.weight, mod.bias)
+
+
+def _attention_block(att, n_heads, x, kv_src, causal):
+    # transformer_blocks.py:119-158 (separate query / key / value projections with bias, c_proj without)
+    q, k, v = _lin(att.query, x), _lin(att.key, kv_src), _lin(att.value, kv_src)
+    return _lin(att.c_proj, Attention.apply(q, k, v, n_heads, causal))
+
+
+def _mlp(m, x):
+    return _lin(m.c_proj, Act.apply(_lin(m.c_fc, x), ACT_GELU))
+
+
+def _check_no_dropout(net):
+    bad = [n for n, m in net.named_modules() if isinstance(m, torch.nn.Dropout) and m.p > 0 and n != "proprio_drop"]
+    if bad or net.cond_mask_prob > 0:
+        raise NotImplementedError(
+            "training path: dropout / goal masking kernels are not implemented yet; configure attn_pdrop = resid_pdrop = mlp_pdrop = "
+            f"embed_pdrob = goal_drop = 0 (non-zero: {bad[:4]}{'...' if len(bad) > 4 else ''}, goal_drop={net.cond_mask_prob})")
+
+
+def encode_train(net, states, goals):
+    """forward_enc_only with gradients (mdtv_transformer.py:213-222 / mdt_transformer.py:211-229)."""
+    if goals.dim() == 2:
+        goals = goals[:, None, :]
+    lang = net.use_modality_encoder and states.get("modality") == "lang" and net._variant == "mdtv"
+    gm = net.lang_emb if lang else net.goal_emb
+    g = _lin(gm[2], Act.apply(_lin(gm[0], goals[:, :1, :].float()), ACT_GELU))
+    if net._variant == "mdtv":
+        s = _lin(net.tok_emb, states["state_images"].float())
+    else:
+        st = _lin(net.tok_emb, states["static"].float())
+        gr = _lin(net.incam_embed, states["gripper"].float())
+        s = torch.cat((st, gr), dim=1)
+        g = g + net.pos_emb[:, : net.goal_seq_len, :]
+        s = s + net.pos_emb[:, net.goal_seq_len: net.goal_seq_len + 1, :]
+    x = torch.cat([g, s], dim=1).contiguous()
+    for blk in net.encoder.blocks:          # Block.forward, transformer_blocks.py:209-214
+        a = LayerNormMod.apply(x, blk.ln_1.weight, blk.ln_1.bias, None, None)
+        x = GateResidual.apply(x, _attention_block(blk.attn, net.n_heads, a, a, False), None)
+        a = LayerNormMod.apply(x, blk.ln_2.weight, blk.ln_2.bias, None, None)
+        x = GateResidual.apply(x, _mlp(blk.mlp, a), None)
+    return LayerNormMod.apply(x, net.encoder.ln.weight, net.encoder.ln.bias, None, None)
+
+
+def decode_train(net, ctx, actions, sigma):
+    """forward_dec_only with gradients (mdtv_transformer.py:224-236, ConditionedBlock :292-309)."""
+    d = net.embed_dim
+    half = d // 2
+    e = sigma.float().log() / 4
+    f = torch.exp(torch.arange(half, device=sigma.device, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    ang = e[:, None] * f[None, :]
+    pe = torch.cat((ang.sin(), ang.cos()), dim=-1)                       # no parameters, no gradient: input preparation
+    c = _lin(net.sigma_emb[3], Act.apply(_lin(net.sigma_emb[1], pe), ACT_MISH))            # (B, d)
+    sc_c = Act.apply(c, ACT_SILU)
+    x = _lin(net.action_emb, actions)
+    for blk in net.decoder.blocks:
+        mod = _lin(blk.adaLN_zero.modulation[1], sc_c)                  # (B, 6d)
+        sh1, s1, g1, sh2, s2, g2 = mod.chunk(6, dim=-1)
+        a = LayerNormMod.apply(x, blk.ln_1.weight, blk.ln_1.bias, sh1, s1)
+        x = GateResidual.apply(x, _attention_block(blk.attn, net.n_heads, a, a, True), g1)
+        a = LayerNormMod.apply(x, blk.ln3.weight, blk.ln3.bias, None, None)
+        x = GateResidual.apply(x, _attention_block(blk.cross_att, net.n_heads, a, ctx, True), None)
+        a = LayerNormMod.apply(x, blk.ln_2.weight, blk.ln_2.bias, sh2, s2)
+        x = GateResidual.apply(x, _mlp(blk.mlp, a), g2)
+    x = LayerNormMod.apply(x, net.decoder.ln.weight, net.decoder.ln.bias, None, None)
+    return _lin(net.action_pred, x)
+
+
+def forward_train(net, states, actions, goals, sigma):
+    _check_no_dropout(net)
+    ctx = encode_train(net, states, goals)
+    net.latent_encoder_emb = ctx
+    return decode_train(net, ctx, _c(actions.float()), sigma)

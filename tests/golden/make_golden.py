@@ -131,6 +131,22 @@ def main():
          ctx=model.forward_context_only(state, x, inp["goal"], sigv),
          ddim=gcs.sample_ddim(model, state, inp["x_T"], inp["goal"], sig, disable=True))
 
+    # ---- training: gradient fingerprints of the reference's GCDenoiser.loss (dropout 0, 2+2 layers, B=16)
+    cfg = ref_shim.mdtv_inner_cfg(n_enc_layers=2, n_dec_layers=2, attn_pdrop=0, resid_pdrop=0, mlp_pdrop=0, embed_pdrob=0, goal_drop=0)
+    model = build(cfg, seed=15, profile="trained").train()
+    inp = synthetic_inputs(16, seed=25)
+    sigma = torch.exp(torch.linspace(3.0, -4.0, 16))
+    with torch.enable_grad():
+        loss, _ = model.loss({"state_images": inp["state_images"], "modality": "lang"}, inp["actions"], inp["goal"], inp["noise"], sigma)
+        loss.backward()
+    norms, probes = [], []
+    for n, p in model.named_parameters():
+        g = p.grad.flatten() if p.grad is not None else torch.zeros(p.numel())
+        norms.append(float(g.norm()))
+        probes.append(g[torch.linspace(0, g.numel() - 1, 8).long()].clone())
+    save("train_grads", meta=dict(case="train_grads", enc=2, dec=2, B=16, weight_seed=15, input_seed=25, profile="trained"),
+         loss=loss.detach(), norms=torch.tensor(norms), probes=torch.stack(probes))
+
     # ---- schedules
     sch = {}
     for n in (1, 3, 5, 10, 20):
