@@ -151,6 +151,124 @@ def cpu_reference_run(enc, dec, B, steps, warmup, budget_s=150.0):
     return value, desc, total / steps * 1e3
 
 
+def train_main(args):
+    """BASELINE config 3 (1 GPU, batch 512) / config 5 (DDP, global batch = 128 x N... here 512 per GPU unless --batch): one step =
+    diffusion loss forward + backward + AdamW update on a synthetic (state tokens, goal, actions) batch.  Metric: action-tokens/s.
+    CPU arm: the same step through autograd over the oracle port."""
+    from mdt_policy_b200 import dist as D
+    rank, local_rank, world = D.env_world()
+    B = args.batch if args.batch != 256 else 512
+    enc = dec = args.layers
+    drop = dict(attn_pdrop=0.3, resid_pdrop=0.1, mlp_pdrop=0.05) if args.dropout else dict(attn_pdrop=0.0, resid_pdrop=0.0, mlp_pdrop=0.0)
+    cfgd = inner_cfg(enc, dec, "fp32", B)
+    cfgd.update(drop)
+    config = {"workload": f"configs[2]: training step, synthetic batch={B}/GPU, MDT-V {enc}enc+{dec}dec, diffusion loss fwd+bwd+AdamW, "
+                          f"dropout {'on (0.3/0.1/0.05)' if args.dropout else 'off'}", "batch_per_gpu": B,
+              "parallelism": f"ddp x{args.gpus}" if args.gpus > 1 else "single"}
+    warmup = max(args.warmup, 3)
+    from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs
+    from mdt_policy_b200 import GCDenoiser, utils as U
+    import math
+
+    def make_batch(seed, device):
+        inp = synthetic_inputs(B, seed=seed)
+        sig = U.rand_log_logistic((B,), loc=math.log(0.5), scale=0.5, min_value=0.001, max_value=80.0, device="cpu")
+        return {k: inp[k].to(device) for k in ("state_images", "goal", "actions", "noise")}, sig.to(device)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import mdt_oracle as orc
+        cores = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(cores)
+        shapes = [(n, p.shape) for n, p in GCDenoiser(cfgd, sigma_data=0.5).named_parameters()]
+        P = {k: v.requires_grad_() for k, v in synthetic_state_dict(shapes, 12, "trained").items()}
+        opt = torch.optim.AdamW(list(P.values()), lr=1e-4, betas=(0.9, 0.9), weight_decay=0.05)
+        ocfg = orc.OracleCfg(n_enc_layers=enc, n_dec_layers=dec)
+        sub = min(B, 64)                                   # bounded sample: a 64-sample slice of the batch per step
+        torch.manual_seed(0)
+        batch, sig = make_batch(31, "cpu")
+        times = []
+        for i in range(min(args.steps, 5) + 1):
+            t0 = time.perf_counter()
+            opt.zero_grad(set_to_none=True)
+            loss, _ = orc.denoiser_loss(P, ocfg, {"state_images": batch["state_images"][:sub], "modality": "lang"}, batch["actions"][:sub],
+                                        batch["goal"][:sub], batch["noise"][:sub], sig[:sub])
+            loss.backward()
+            opt.step()
+            times.append(time.perf_counter() - t0)
+        t = sum(times[1:]) / (len(times) - 1)
+        value = sub * 10 / t
+        desc = {"value": value, "unit": "action-tokens/s", "cores": cores, "kind": "port",
+                "sample": f"{len(times) - 1} steps on {sub} of {B} samples, dropout off (the port has no dropout), {t * 1e3:.0f} ms per step"}
+        print(json.dumps({"impl": "reference", "metric": "training action-tokens/sec (diffusion loss fwd+bwd+AdamW)", "value": value,
+                          "unit": "action-tokens/s", "n_gpus": args.gpus, "steps": len(times) - 1, "warmup": 1, "ms_per_step": t * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config, "cpu_baseline": desc,
+                          "e2e": {"value": value, "unit": "action-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    rank, local_rank, world = D.init_from_env("nccl")
+    model = GCDenoiser(cfgd, sigma_data=0.5)
+    model.load_state_dict(synthetic_state_dict([(n, p.shape) for n, p in model.named_parameters()], 12, "trained"))
+    model = model.to(dev).train()
+
+    class LossModule(torch.nn.Module):            # DDP needs the work to go through forward()
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, state_images, goal, actions, noise, sigma):
+            return self.m.loss({"state_images": state_images, "modality": "lang"}, actions, goal, noise, sigma)[0]
+
+    net = LossModule(model)
+    if world > 1:
+        # pos_emb / proprio_emb / goal_emb (lang batches) get no gradient: exactly the reference's situation under Lightning DDP
+        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], find_unused_parameters=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=0.05)
+    torch.manual_seed(rank)
+    batch, sig = make_batch(31 + rank, dev)
+
+    def step(sync=True):
+        opt.zero_grad(set_to_none=True)
+        ctxm = net.no_sync() if (world > 1 and not sync) else __import__("contextlib").nullcontext()
+        with ctxm:
+            loss = net(batch["state_images"], batch["goal"], batch["actions"], batch["noise"], sig)
+            loss.backward()
+        opt.step()
+        return loss
+
+    def timed(k, sync=True):
+        D.barrier(); torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            step(sync)
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / 1e3
+
+    for _ in range(warmup):
+        step()
+    t = timed(args.steps)
+    t_nosync = timed(args.steps, sync=False) if world > 1 else t
+    agg = D.aggregate_throughput(args.steps * B * 10, t, device=dev)
+    last = float(step())
+    D.shutdown()
+    if rank != 0:
+        return 0
+    fwd_flops = B * (F_ENC * enc / 4 + F_KV * dec / 4 + (F_CORE - 107_520) * dec / 4 + 107_520 + 1_179_648 + 1_769_472 * dec)
+    print(json.dumps({
+        "metric": "training action-tokens/sec (diffusion loss fwd+bwd+AdamW)", "value": agg["throughput"], "unit": "action-tokens/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": agg["seconds"] / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CUDA cores, exact)", "data": "synthetic", "config": config,
+        "exposed_comm_ms": max(0.0, (t - t_nosync) / args.steps * 1e3) if world > 1 else 0.0, "final_loss": last,
+        "roofline": {"bound": "fp32 CUDA cores (training path is not on tensor cores yet)", "achieved": 3 * fwd_flops / (t / args.steps) / 1e12,
+                     "unit": "TFLOP/s", "note": "3 x forward algorithmic FLOPs per step"}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,7 +279,12 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="environments per GPU")
     ap.add_argument("--layers", type=int, default=4, help="4 = shipped MDT-V yaml (4 enc + 4 dec); 6 = BASELINE-literal 6+6")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample = the headline metric (default); train = BASELINE configs 3/5: GCDenoiser.loss fwd+bwd+AdamW step")
+    ap.add_argument("--dropout", type=int, default=1, help="train workload: 1 = shipped dropout probabilities, 0 = all zero")
     args = ap.parse_args()
+    if args.workload == "train":
+        return train_main(args)
     enc = dec = args.layers
     B = args.batch
     workload = (f"configs[1]: full {N_STEPS}-step EDM/DDIM sampling, batch={B}/GPU, MDT-V d=384 h=8 {enc}enc+{dec}dec, "

@@ -156,11 +156,14 @@ MDTB200_API int mdtb200_op_ln_fwd(const float* x, const float* w, const float* b
 MDTB200_API int mdtb200_op_ln_bwd(const float* x, const float* dy, const float* w, const float* b, const float* scale,
                                   int mod_stride, int rows_per_group, int M, int d, float* dx, float* t_dw, float* t_db,
                                   float* t_dsc, void* stream);
+/* p_drop / seed: dropout on the attention probabilities (transformer_blocks.py:142); the mask is a pure function of
+ * (seed, element index), so the backward call with the same pair regenerates it */
 MDTB200_API int mdtb200_op_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* y, int ldy,
-                                    int B, int H, int hd, int Tq, int Tk, int causal, void* stream);
+                                    int B, int H, int hd, int Tq, int Tk, int causal, float p_drop, uint64_t seed, void* stream);
 MDTB200_API int mdtb200_op_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dy, int lddy,
                                     float* dq, int lddq, float* dk, float* dv, int lddkv, int B, int H, int hd, int Tq, int Tk,
-                                    int causal, void* stream);
+                                    int causal, float p_drop, uint64_t seed, void* stream);
+MDTB200_API int mdtb200_op_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
 MDTB200_API int mdtb200_op_gate_res(const float* x, const float* f, const float* gate, float* out, int M, int d,
                                     int rows_per_group, void* stream);
 MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const float* gate, float* df, float* prod, int M, int d,

@@ -22,7 +22,7 @@ EXPORTS = [
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
     "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time",
     "mdtb200_op_gemm", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
-    "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd",
+    "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout",
 ]
 
 
@@ -77,11 +77,12 @@ def _declare(lib):
     lib.mdtb200_op_act.argtypes = [fp, fp, fp, i64, i32, vp]
     lib.mdtb200_op_ln_fwd.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, i32, fp, vp]
     lib.mdtb200_op_ln_bwd.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, i32, fp, fp, fp, fp, vp]
-    lib.mdtb200_op_attn_fwd.argtypes = [fp, i32, fp, fp, i32, fp, i32, i32, i32, i32, i32, i32, i32, vp]
-    lib.mdtb200_op_attn_bwd.argtypes = [fp, i32, fp, fp, i32, fp, i32, fp, i32, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mdtb200_op_attn_fwd.argtypes = [fp, i32, fp, fp, i32, fp, i32, i32, i32, i32, i32, i32, i32, C.c_float, C.c_uint64, vp]
+    lib.mdtb200_op_attn_bwd.argtypes = [fp, i32, fp, fp, i32, fp, i32, fp, i32, fp, fp, i32, i32, i32, i32, i32, i32, i32, C.c_float, C.c_uint64, vp]
+    lib.mdtb200_op_dropout.argtypes = [fp, fp, i64, C.c_float, C.c_uint64, vp]
     lib.mdtb200_op_gate_res.argtypes = [fp, fp, fp, fp, i32, i32, i32, vp]
     lib.mdtb200_op_gate_res_bwd.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, vp]
-    for _n in ("gemm", "group_sum", "colsum", "act", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "gate_res", "gate_res_bwd"):
+    for _n in ("gemm", "group_sum", "colsum", "act", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "gate_res", "gate_res_bwd", "dropout"):
         getattr(lib, "mdtb200_op_" + _n).restype = i32
     return lib
 

@@ -313,7 +313,20 @@ struct AttnArgs {
   __nv_bfloat16* y16; int ld16; int lo_off;  // split-bf16 out (may be null)
   int B, H, hd, Tq, Tk, causal;
   float scale;
+  float p_drop; unsigned long long seed;      // training only: dropout on the attention probabilities (generic kernel)
 };
+
+// counter-based uniform in [0,1): splitmix64 of (seed, element index).  Forward and backward regenerate the same mask.
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p) {
+  return hash_uniform(seed, idx) >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
 
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_MAXT = 16, ATT_MAXHD = 64;
@@ -370,6 +383,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
     for (int j = 0; j < Tk; ++j) { float ex = expf(row[j] - mx); row[j] = ex; sum += ex; }
     const float inv = 1.0f / sum;
     for (int j = 0; j < Tk; ++j) row[j] *= inv;
+    if (a.p_drop > 0.f) {     // tid = h * Tq + i
+      const unsigned long long base = ((unsigned long long)b * a.H * Tq + tid) * Tk;
+      for (int j = 0; j < Tk; ++j) row[j] *= dropout_scale(a.seed, base + j, a.p_drop);
+    }
   }
   __syncthreads();
   for (int e = tid; e < Tq * D; e += ATT_THREADS) {

@@ -177,6 +177,13 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
   dx[i] = dy[i] * d;
 }
 
+// inverted dropout with a regenerable mask: out = x * [u(seed, i) >= p] / (1 - p)   (forward on x, backward on dy)
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long n, float p, unsigned long long seed) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = x[i] * dropout_scale(seed, (unsigned long long)i, p);
+}
+
 // out = x + gate[g] * f  (gate may be null: out = x + f), g = row / rows_per_group
 __global__ void gate_res_fwd_kernel(const float* __restrict__ x, const float* __restrict__ f, const float* __restrict__ gate,
                                     float* __restrict__ out, int M, int d, int rows_per_group) {
@@ -269,10 +276,11 @@ struct AttnBwdArgs {
   const float* q; int ldq; const float* k; const float* v; int ldkv; const float* dy; int lddy;
   float* dq; int lddq; float* dk; float* dv; int lddkv;
   int B, H, hd, Tq, Tk, causal; float scale;
+  float p_drop; unsigned long long seed;     // dropout on the probabilities: same mask as the forward kernel
 };
 __global__ void __launch_bounds__(128) attention_bwd_kernel(AttnBwdArgs a) {
   __shared__ float sq[ATT_MAXT][ATT_MAXHD + 1], sk[ATT_MAXT][ATT_MAXHD + 1], sv[ATT_MAXT][ATT_MAXHD + 1], sdy[ATT_MAXT][ATT_MAXHD + 1];
-  __shared__ float sp[ATT_MAXT][ATT_MAXT + 1], sds[ATT_MAXT][ATT_MAXT + 1];
+  __shared__ float sp[ATT_MAXT][ATT_MAXT + 1], sds[ATT_MAXT][ATT_MAXT + 1], spu[ATT_MAXT][ATT_MAXT + 1];
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, tid = threadIdx.x;
   const int hd = a.hd, Tq = a.Tq, Tk = a.Tk;
   for (int e = tid; e < Tq * hd; e += blockDim.x) {
@@ -301,7 +309,14 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(AttnBwdArgs a) {
     for (int j = 0; j < Tk; ++j) { float ex = expf(sp[tid][j] - mx); sp[tid][j] = ex; sum += ex; }
     const float inv = 1.0f / sum;
     float dot = 0.f;
-    for (int j = 0; j < Tk; ++j) { sp[tid][j] *= inv; dot += sds[tid][j] * sp[tid][j]; }
+    const unsigned long long base = ((unsigned long long)b * a.H * Tq + (unsigned long long)h * Tq + tid) * Tk;
+    for (int j = 0; j < Tk; ++j) {
+      sp[tid][j] *= inv;
+      const float m = a.p_drop > 0.f ? dropout_scale(a.seed, base + j, a.p_drop) : 1.0f;   // P_used = P * m
+      spu[tid][j] = sp[tid][j] * m;
+      sds[tid][j] *= m;                         // dP = dP_used * m
+      dot += sds[tid][j] * sp[tid][j];
+    }
     for (int j = 0; j < Tk; ++j) sds[tid][j] = sp[tid][j] * (sds[tid][j] - dot) * a.scale;   // dS (scaled)
   }
   __syncthreads();
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(AttnBwdArgs a) {
   for (int e = tid; e < Tk * hd; e += blockDim.x) {          // dK = dS^T Q ; dV = P^T dY
     const int j = e / hd, c = e % hd;
     float ok = 0.f, ov = 0.f;
-    for (int i = 0; i < Tq; ++i) { ok = fmaf(sds[i][j], sq[i][c], ok); ov = fmaf(sp[i][j], sdy[i][c], ov); }
+    for (int i = 0; i < Tq; ++i) { ok = fmaf(sds[i][j], sq[i][c], ok); ov = fmaf(spu[i][j], sdy[i][c], ov); }
     a.dk[(size_t)(b * Tk + j) * a.lddkv + h * hd + c] = ok;
     a.dv[(size_t)(b * Tk + j) * a.lddkv + h * hd + c] = ov;
   }

@@ -136,12 +136,14 @@ MDTB200_API int mdtb200_op_ln_bwd(const float* x, const float* dy, const float* 
 
 // softmax(q k^T / sqrt(hd) + causal-top-left mask) v for T <= 16; strided operands (row stride in floats)
 MDTB200_API int mdtb200_op_attn_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* y, int ldy, int B, int H, int hd,
-                                    int Tq, int Tk, int causal, void* stream) {
+                                    int Tq, int Tk, int causal, float p_drop, uint64_t seed, void* stream) {
   if (!q || !k || !v || !y || B < 1 || H < 1 || hd < 4 || hd % 4 || hd > ATT_MAXHD || Tq < 1 || Tq > ATT_MAXT || Tk < 1 || Tk > ATT_MAXT)
     return op_fail(MDTB200_EINVAL, "op_attn_fwd: bad argument");
   AttnArgs a{};
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = ldy; a.B = B; a.H = H; a.hd = hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
   a.scale = 1.0f / sqrtf((float)hd);
+  a.p_drop = p_drop; a.seed = seed;
+  if (!(p_drop >= 0.f && p_drop < 1.f)) return op_fail(MDTB200_EINVAL, "op_attn_fwd: p_drop must be in [0, 1)");
   const size_t smem = attention_smem_bytes(H * hd, H, Tq, Tk);
   static size_t configured = 0;
   if (smem > configured) {
@@ -153,12 +155,20 @@ MDTB200_API int mdtb200_op_attn_fwd(const float* q, int ldq, const float* k, con
 }
 
 MDTB200_API int mdtb200_op_attn_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dy, int lddy, float* dq,
-                                    int lddq, float* dk, float* dv, int lddkv, int B, int H, int hd, int Tq, int Tk, int causal, void* stream) {
+                                    int lddq, float* dk, float* dv, int lddkv, int B, int H, int hd, int Tq, int Tk, int causal, float p_drop,
+                                    uint64_t seed, void* stream) {
   if (!q || !k || !v || !dy || !dq || !dk || !dv || B < 1 || H < 1 || hd < 1 || hd > ATT_MAXHD || Tq < 1 || Tq > ATT_MAXT || Tk < 1 || Tk > ATT_MAXT)
     return op_fail(MDTB200_EINVAL, "op_attn_bwd: bad argument");
-  AttnBwdArgs a{q, ldq, k, v, ldkv, dy, lddy, dq, lddq, dk, dv, lddkv, B, H, hd, Tq, Tk, causal, 1.0f / sqrtf((float)hd)};
+  AttnBwdArgs a{q, ldq, k, v, ldkv, dy, lddy, dq, lddq, dk, dv, lddkv, B, H, hd, Tq, Tk, causal, 1.0f / sqrtf((float)hd), p_drop, seed};
   attention_bwd_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(a);
   return op_check("attention_bwd_kernel");
+}
+
+// inverted dropout with a mask that is a pure function of (seed, element index): the same call on dy is the backward
+MDTB200_API int mdtb200_op_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream) {
+  if (!x || !out || n < 1 || !(p >= 0.f && p < 1.f)) return op_fail(MDTB200_EINVAL, "op_dropout: bad argument");
+  dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, (long)n, p, seed);
+  return op_check("dropout_kernel");
 }
 
 // out = x + gate[row / rows_per_group] * f   (gate NULL: out = x + f)

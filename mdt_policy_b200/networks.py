@@ -276,7 +276,8 @@ class _ScoreNetBase(nn.Module):
         if self.training and (self.cond_mask_prob > 0 or any(
                 isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules())):
             raise NotImplementedError(
-                "train-mode forward (dropout / goal masking) is not implemented by the CUDA path yet; call .eval()")
+                "train-mode forward under torch.no_grad(): the inference kernels implement eval semantics only (no dropout / goal "
+                "masking); call .eval(), or enable autograd to run the training path (mdt_policy_b200/training.py)")
 
     # -- reference API ---------------------------------------------------------------------------------------------
     def _encode(self, states, goals, uncond, context_only, want_ctx=True):
@@ -330,7 +331,6 @@ class _ScoreNetBase(nn.Module):
     def forward_enc_only(self, states, actions=None, goals=None, sigma=None, uncond: Optional[bool] = False):
         if self.wants_grad(goals) and self._variant == "mdtv":
             from . import training
-            training._check_no_dropout(self)
             return training.encode_train(self, states, torch.zeros_like(goals) if uncond else goals)
         _, ctx = self._encode(states, goals, uncond, context_only=True)
         return ctx

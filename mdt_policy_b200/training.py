@@ -4,8 +4,11 @@ mdtv_transformer.py:208-236 -> transformer_blocks.py Block / ConditionedBlock / 
 The graph is held by torch.autograd (plumbing: saved tensors, gradient accumulation over the residual stream and the
 shared sigma embedding), but every node is one of the autograd Functions below whose forward AND backward are the
 exact-fp32 CUDA kernels of libmdtb200.so (C ABI "training primitives": mdtb200_op_*).  Semantics are the reference's
-train-mode forward with all dropout probabilities and goal_drop equal to 0 -- dropout kernels are not implemented yet and
-a model configured with p > 0 raises instead of silently training without it.
+train-mode forward: dropout on the attention probabilities (attn_pdrop), after both c_proj projections (resid_pdrop,
+mlp_pdrop) and on the action embedding (embed_pdrob), goal masking (goal_drop).  Dropout masks come from a counter-based
+hash of (seed, element index) -- the seed of every site is drawn from torch's CPU generator, so torch.manual_seed makes a
+step reproducible -- and cannot equal the reference's Philox stream: with p = 0 gradients match the reference to fp32
+rounding, with p > 0 the check is statistical (tests/test_gpu_training.py).
 """
 from __future__ import annotations
 
@@ -147,33 +150,63 @@ class LayerNormMod(Function):
         return dx, dw, db, dshift, dscale
 
 
-class Attention(Function):
-    """softmax(q k^T / sqrt(hd) + mask) v over heads; q (B,Tq,D), k/v (B,Tk,D)."""
+def _new_seed() -> int:
+    """one 63-bit seed per dropout site and call, from torch's CPU generator (torch.manual_seed -> reproducible)"""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+class Dropout(Function):
+    """inverted dropout; the mask is a pure function of (seed, element index), regenerated in backward"""
 
     @staticmethod
-    def forward(ctx, q, k, v, n_heads, causal):
+    def forward(ctx, x, p, seed):
+        _require_cuda(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        _chk(_lib.load().mdtb200_op_dropout(_p(x), _p(y), x.numel(), float(p), seed, _stream(x)), "op_dropout")
+        ctx.cfg = (float(p), seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        _chk(_lib.load().mdtb200_op_dropout(_p(dy), _p(dx), dy.numel(), p, seed, _stream(dy)), "op_dropout bwd")
+        return dx, None, None
+
+
+def _drop(x, p):
+    return Dropout.apply(x, p, _new_seed()) if p > 0 else x
+
+
+class Attention(Function):
+    """softmax(q k^T / sqrt(hd) + mask) v over heads, optional dropout on the probabilities; q (B,Tq,D), k/v (B,Tk,D)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, n_heads, causal, p_drop, seed):
         _require_cuda(q)
         q, k, v = _c(q), _c(k), _c(v)
         B, Tq, D = q.shape
         Tk = k.shape[1]
         y = torch.empty_like(q)
         _chk(_lib.load().mdtb200_op_attn_fwd(_p(q), D, _p(k), _p(v), D, _p(y), D, B, n_heads, D // n_heads, Tq, Tk, int(causal),
-                                             _stream(q)), "op_attn_fwd")
+                                             float(p_drop), seed, _stream(q)), "op_attn_fwd")
         ctx.save_for_backward(q, k, v)
-        ctx.cfg = (n_heads, int(causal))
+        ctx.cfg = (n_heads, int(causal), float(p_drop), seed)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         q, k, v = ctx.saved_tensors
-        H, causal = ctx.cfg
+        H, causal, p_drop, seed = ctx.cfg
         B, Tq, D = q.shape
         Tk = k.shape[1]
         dy = _c(dy)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         _chk(_lib.load().mdtb200_op_attn_bwd(_p(q), D, _p(k), _p(v), D, _p(dy), D, _p(dq), D, _p(dk), _p(dv), D, B, H, D // H, Tq, Tk,
-                                             causal, _stream(q)), "op_attn_bwd")
-        return dq, dk, dv, None, None
+                                             causal, p_drop, seed, _stream(q)), "op_attn_bwd")
+        return dq, dk, dv, None, None, None, None
 
 
 class GateResidual(Function):
@@ -209,28 +242,40 @@ def _lin(mod, x):
     return Linear.apply(x, mod.weight, mod.bias)
 
 
-def _attention_block(att, n_heads, x, kv_src, causal):
-    # transformer_blocks.py:119-158 (separate query / key / value projections with bias, c_proj without)
+def _attention_block(att, n_heads, x, kv_src, causal, train):
+    # transformer_blocks.py:119-158: separate query / key / value projections with bias, SDPA with dropout_p = attn_pdrop in
+    # train mode, c_proj (no bias) followed by resid_dropout
     q, k, v = _lin(att.query, x), _lin(att.key, kv_src), _lin(att.value, kv_src)
-    return _lin(att.c_proj, Attention.apply(q, k, v, n_heads, causal))
+    pa = att.attn_dropout.p if train else 0.0
+    y = Attention.apply(q, k, v, n_heads, causal, pa, _new_seed() if pa > 0 else 0)
+    return _drop(_lin(att.c_proj, y), att.resid_dropout.p if train else 0.0)
 
 
-def _mlp(m, x):
-    return _lin(m.c_proj, Act.apply(_lin(m.c_fc, x), ACT_GELU))
+def _mlp(m, x, train):
+    # transformer_blocks.py:175-180
+    return _drop(_lin(m.c_proj, Act.apply(_lin(m.c_fc, x), ACT_GELU)), m.dropout.p if train else 0.0)
 
 
 def _check_no_dropout(net):
+    """kept for callers that need the dropout-free semantics (gradient parity tests)"""
     bad = [n for n, m in net.named_modules() if isinstance(m, torch.nn.Dropout) and m.p > 0 and n != "proprio_drop"]
-    if bad or net.cond_mask_prob > 0:
-        raise NotImplementedError(
-            "training path: dropout / goal masking kernels are not implemented yet; configure attn_pdrop = resid_pdrop = mlp_pdrop = "
-            f"embed_pdrob = goal_drop = 0 (non-zero: {bad[:4]}{'...' if len(bad) > 4 else ''}, goal_drop={net.cond_mask_prob})")
+    if net.training and (bad or net.cond_mask_prob > 0):
+        raise RuntimeError(f"dropout is active ({bad[:3]}...)")
+
+
+def _mask_goal(net, goals):
+    # mask_cond, mdtv_transformer.py:302-309 (input preparation: element-wise Bernoulli mask on the goal embedding)
+    if net.training and net.cond_mask_prob > 0:
+        return goals * (1.0 - torch.bernoulli(torch.full_like(goals, net.cond_mask_prob)))
+    return goals
 
 
 def encode_train(net, states, goals):
     """forward_enc_only with gradients (mdtv_transformer.py:213-222 / mdt_transformer.py:211-229)."""
     if goals.dim() == 2:
         goals = goals[:, None, :]
+    goals = _mask_goal(net, goals)
+    train = net.training
     lang = net.use_modality_encoder and states.get("modality") == "lang" and net._variant == "mdtv"
     gm = net.lang_emb if lang else net.goal_emb
     g = _lin(gm[2], Act.apply(_lin(gm[0], goals[:, :1, :].float()), ACT_GELU))
@@ -245,9 +290,9 @@ def encode_train(net, states, goals):
     x = torch.cat([g, s], dim=1).contiguous()
     for blk in net.encoder.blocks:          # Block.forward, transformer_blocks.py:209-214
         a = LayerNormMod.apply(x, blk.ln_1.weight, blk.ln_1.bias, None, None)
-        x = GateResidual.apply(x, _attention_block(blk.attn, net.n_heads, a, a, False), None)
+        x = GateResidual.apply(x, _attention_block(blk.attn, net.n_heads, a, a, False, train), None)
         a = LayerNormMod.apply(x, blk.ln_2.weight, blk.ln_2.bias, None, None)
-        x = GateResidual.apply(x, _mlp(blk.mlp, a), None)
+        x = GateResidual.apply(x, _mlp(blk.mlp, a, train), None)
     return LayerNormMod.apply(x, net.encoder.ln.weight, net.encoder.ln.bias, None, None)
 
 
@@ -261,22 +306,22 @@ def decode_train(net, ctx, actions, sigma):
     pe = torch.cat((ang.sin(), ang.cos()), dim=-1)                       # no parameters, no gradient: input preparation
     c = _lin(net.sigma_emb[3], Act.apply(_lin(net.sigma_emb[1], pe), ACT_MISH))            # (B, d)
     sc_c = Act.apply(c, ACT_SILU)
-    x = _lin(net.action_emb, actions)
+    train = net.training
+    x = _drop(_lin(net.action_emb, actions), net.drop.p if train else 0.0)
     for blk in net.decoder.blocks:
         mod = _lin(blk.adaLN_zero.modulation[1], sc_c)                  # (B, 6d)
         sh1, s1, g1, sh2, s2, g2 = mod.chunk(6, dim=-1)
         a = LayerNormMod.apply(x, blk.ln_1.weight, blk.ln_1.bias, sh1, s1)
-        x = GateResidual.apply(x, _attention_block(blk.attn, net.n_heads, a, a, True), g1)
+        x = GateResidual.apply(x, _attention_block(blk.attn, net.n_heads, a, a, True, train), g1)
         a = LayerNormMod.apply(x, blk.ln3.weight, blk.ln3.bias, None, None)
-        x = GateResidual.apply(x, _attention_block(blk.cross_att, net.n_heads, a, ctx, True), None)
+        x = GateResidual.apply(x, _attention_block(blk.cross_att, net.n_heads, a, ctx, True, train), None)
         a = LayerNormMod.apply(x, blk.ln_2.weight, blk.ln_2.bias, sh2, s2)
-        x = GateResidual.apply(x, _mlp(blk.mlp, a), g2)
+        x = GateResidual.apply(x, _mlp(blk.mlp, a, train), g2)
     x = LayerNormMod.apply(x, net.decoder.ln.weight, net.decoder.ln.bias, None, None)
     return _lin(net.action_pred, x)
 
 
 def forward_train(net, states, actions, goals, sigma):
-    _check_no_dropout(net)
     ctx = encode_train(net, states, goals)
     net.latent_encoder_emb = ctx
     return decode_train(net, ctx, _c(actions.float()), sigma)

@@ -95,8 +95,11 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
         GCDenoiser(H.mdtv_inner_cfg(use_rot_embed=True))
     model = GCDenoiser(H.mdtv_inner_cfg(n_enc=1, n_dec=1)).train()
-    with pytest.raises(NotImplementedError, match="train-mode"):
-        model({"state_images": torch.zeros(1, 3, 384)}, torch.zeros(1, 10, 7), torch.zeros(1, 1, 512), torch.ones(1))
+    args = ({"state_images": torch.zeros(1, 3, 384)}, torch.zeros(1, 10, 7), torch.zeros(1, 1, 512), torch.ones(1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):       # autograd on -> training path, CUDA only
+        model(*args)
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="train-mode"):   # the inference kernels have no dropout
+        model(*args)
 
 
 def test_schedules_bit_equal_reference():

@@ -80,7 +80,7 @@ def test_attention_fwd_bwd(Tq, Tk, causal, hd):
     y = torch.nn.functional.scaled_dot_product_attention(sp(q, Tq), sp(k, Tk), sp(v, Tk), attn_mask=mask).transpose(1, 2).reshape(B, Tq, D)
     y.backward(dy)
     qc, kc, vc = (t.detach().float().cuda().requires_grad_() for t in (q, k, v))
-    yc = T.Attention.apply(qc, kc, vc, Hh, causal)
+    yc = T.Attention.apply(qc, kc, vc, Hh, causal, 0.0, 0)
     yc.backward(dy.float().cuda())
     assert _rel(yc, y) < 5e-6 and _rel(qc.grad, q.grad) < 2e-5 and _rel(kc.grad, k.grad) < 2e-5 and _rel(vc.grad, v.grad) < 2e-5
 
@@ -192,3 +192,74 @@ def test_optimizer_step_reduces_loss_and_resyncs_inference_weights():
     with torch.enable_grad():
         l_tr, _ = model.loss(state, inp["actions"], inp["goal"], inp["noise"], sigma)
     assert abs(float(l_inf) - float(l_tr)) < 1e-3 * max(1.0, float(l_tr))
+
+
+def test_dropout_ops_mask_consistency():
+    """Element dropout: keep fraction ~ 1-p, kept values scaled by 1/(1-p), backward uses the SAME mask.  Attention dropout:
+    with V = one-hot the output reveals the (dropped, rescaled) probabilities; forward and backward agree with a torch
+    computation that applies that very mask."""
+    x = torch.randn(1 << 18, device="cuda", requires_grad=True)
+    y = T.Dropout.apply(x, 0.3, 12345)
+    keep = (y != 0)
+    assert abs(float(keep.float().mean()) - 0.7) < 0.01
+    assert torch.allclose(y[keep], x.detach()[keep] / 0.7, rtol=1e-6)
+    y.backward(torch.ones_like(y))
+    assert torch.equal(x.grad != 0, keep) and torch.allclose(x.grad[keep], torch.full_like(x.grad[keep], 1 / 0.7))
+    assert not torch.equal(T.Dropout.apply(x.detach(), 0.3, 999) != 0, keep)        # another seed, another mask
+
+    B, Hh, Tq, Tk, hd = 3, 8, 10, 10, 16
+    D = Hh * hd
+    g = torch.Generator().manual_seed(3)
+    q, k = (torch.randn(B, t, D, generator=g).cuda() for t in (Tq, Tk))
+    v_onehot = torch.zeros(B, Tk, Hh, hd); v_onehot[:, torch.arange(Tk), :, torch.arange(Tk)] = 1.0     # v[b, j, h, c] = (c == j)
+    p_used = T.Attention.apply(q, k, v_onehot.view(B, Tk, D).cuda(), Hh, True, 0.3, 777).view(B, Tq, Hh, hd)[..., :Tk]   # (B,Tq,H,Tk)
+    sp = lambda t, n: t.view(B, n, Hh, hd).transpose(1, 2)
+    s = (sp(q, Tq) @ sp(k, Tk).transpose(-1, -2)) / hd ** 0.5
+    mask = torch.arange(Tk, device="cuda")[None, :] <= torch.arange(Tq, device="cuda")[:, None]
+    P = torch.softmax(s.masked_fill(~mask, float("-inf")), dim=-1)                  # (B,H,Tq,Tk)
+    pu = p_used.permute(0, 2, 1, 3)
+    m = torch.where(pu != 0, torch.full_like(pu, 1 / 0.7), torch.zeros_like(pu))
+    live = P > 1e-6
+    assert torch.allclose(pu[live & (pu != 0)], (P * m)[live & (pu != 0)], rtol=2e-5, atol=1e-7)
+    assert abs(float((pu[live] != 0).float().mean()) - 0.7) < 0.05
+    # gradients with the same mask
+    v = torch.randn(B, Tk, D, generator=g).cuda()
+    qa, ka, va = (t.clone().requires_grad_() for t in (q, k, v))
+    ya = T.Attention.apply(qa, ka, va, Hh, True, 0.3, 777)
+    dy = torch.randn(B, Tq, D, generator=g).cuda()
+    ya.backward(dy)
+    qb, kb, vb = (t.clone().double().requires_grad_() for t in (q, k, v))
+    sb = (sp(qb, Tq) @ sp(kb, Tk).transpose(-1, -2)) / hd ** 0.5
+    Pb = torch.softmax(sb.masked_fill(~mask, float("-inf")), dim=-1) * m.double()
+    yb = (Pb @ sp(vb, Tk)).transpose(1, 2).reshape(B, Tq, D)
+    yb.backward(dy.double())
+    assert _rel(ya, yb) < 5e-6 and _rel(qa.grad, qb.grad) < 2e-5 and _rel(ka.grad, kb.grad) < 2e-5 and _rel(va.grad, vb.grad) < 2e-5
+
+
+def test_training_with_shipped_dropout_probabilities():
+    """The shipped config (attn 0.3 / resid 0.1 / mlp 0.05) trains: finite loss and gradients, reproducible under
+    torch.manual_seed, different under another seed, and the mean loss over seeds is close to the dropout-free loss scale."""
+    model = H.build_product(H.mdtv_inner_cfg(2, 2), 97, "trained").train()
+    inp = {k: v.cuda() for k, v in synthetic_inputs(32, seed=98).items()}
+    sigma = torch.exp(torch.linspace(2.0, -3.0, 32)).cuda()
+    state = {"state_images": inp["state_images"], "modality": "lang"}
+
+    def run(seed):
+        torch.manual_seed(seed)
+        model.zero_grad(set_to_none=True)
+        loss, _ = model.loss(state, inp["actions"], inp["goal"], inp["noise"], sigma)
+        loss.backward()
+        return float(loss), model.inner_model.decoder.blocks[0].mlp.c_fc.weight.grad.clone()
+
+    l1, g1 = run(1)
+    l1b, g1b = run(1)
+    l2, g2 = run(2)
+    assert l1 == l1b and torch.equal(g1, g1b)
+    assert l1 != l2 and not torch.equal(g1, g2)
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    model.eval()
+    with torch.no_grad():
+        l_eval = float(model.loss(state, inp["actions"], inp["goal"], inp["noise"], sigma)[0])
+    model.train()
+    mean_l = sum(run(s)[0] for s in range(3, 9)) / 6
+    assert 0.3 * l_eval < mean_l < 3.0 * l_eval
