@@ -87,6 +87,29 @@ class DenoiseAgent:
         """End-to-end call on HOST tensors (pinned or not): H2D copies of the inputs, the sampling graph, D2H copy
         of the actions, one synchronisation.  This is the call bench.py's ``e2e`` number times."""
         dev = self.device
+        inner = getattr(self.model, "inner_model", None)
+        fused = self.sampler_type in ("ddim", "euler", "heun", "dpmpp_2m") and getattr(inner, "_variant", None) == "mdtv"
+        if (fused and not state_images_host.is_cuda and state_images_host.dtype == torch.float32 and state_images_host.is_contiguous()
+                and latent_goal_host.is_contiguous() and x_T_host.is_contiguous()):
+            # straight through the C ABI's host-buffer entry point: no intermediate CUDA tensors on the Python side
+            self.model.eval()
+            key = ("host", self.num_sampling_steps, self.noise_scheduler, self.sigma_min, self.sigma_max)
+            cache = self.__dict__.setdefault("_schedule_cache", {})
+            if key not in cache:
+                dev_saved, self.device = self.device, torch.device("cpu")
+                try:
+                    cache[key] = self._build_noise_schedule(self.num_sampling_steps, self.noise_scheduler).float().contiguous()
+                finally:
+                    self.device = dev_saved
+            goal2d = latent_goal_host.reshape(latent_goal_host.shape[0], -1)
+            if goal2d.shape[1] != inner.goal_dim or state_images_host.shape[1:] != (inner.n_state_tokens, inner.obs_dim) \
+                    or x_T_host.shape != (goal2d.shape[0], inner.action_seq_len, inner.action_dim):
+                raise ValueError("denoise_actions_host: input shapes do not match the model configuration")
+            if out_host is None:
+                out_host = torch.empty(x_T_host.shape, dtype=torch.float32, pin_memory=True)
+            out_host.copy_(x_T_host)
+            modality_lang = inner.use_modality_encoder and modality == "lang"
+            return inner.sample_host(state_images_host, out_host, goal2d, cache[key], self.sampler_type, modality_lang, dev)
         state = {"state_images": state_images_host.to(dev, non_blocking=True), "modality": modality}
         goal = latent_goal_host.to(dev, non_blocking=True)
         x_T = x_T_host.to(dev, non_blocking=True)

@@ -957,10 +957,6 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
     }
   }
   if (trace) cudaFree(trace);
-  if (!rc && e == cudaSuccess) {
-    // fold the split-bf16 copy back (hi + lo) into the second half of `out` is not possible (size); verify it here instead:
-    // out16[m,n] = hi + lo must reproduce out within 2^-16 relative -- checked by the caller through mdtb200_debug_copy-free path
-  }
   h->tma.cache.clear();
   cudaFree(a16); cudaFree(w16); cudaFree(c16);
   if (rc) return rc;

@@ -360,6 +360,20 @@ class _ScoreNetBase(nn.Module):
         return x
 
 
+    def sample_host(self, state_host, x_inout_host, goal_host, sigmas_host, sampler: str, modality_lang: bool, device):
+        """Whole sampling call on HOST buffers through mdtb200_sample_host: the library stages state/goal/x_T/sigmas to the
+        device, replays the graph and copies the actions back into `x_inout_host` (synchronous on return)."""
+        self._check_mode()
+        B = state_host.shape[0]
+        eng = self._engine(device, B)
+        n_steps = sigmas_host.numel() - 1
+        with torch.cuda.device(eng.device):
+            eng.check(eng.lib.mdtb200_sample_host(eng.handle, _lib.SAMPLER[sampler], _ptr(sigmas_host), n_steps, _ptr(goal_host),
+                                                  _ptr(state_host), _lib.MODALITY_LANG if modality_lang else _lib.MODALITY_VIS, B,
+                                                  _ptr(x_inout_host), eng.stream), "mdtb200_sample_host")
+        return x_inout_host
+
+
 class MDTVTransformer(_ScoreNetBase):
     """Drop-in for mdt.models.networks.mdtv_transformer.MDTVTransformer (same ctor arguments)."""
 
