@@ -147,6 +147,11 @@ MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* ds
 /* mode 0: C[M,N] = A[M,K] B[N,K]^T (+bias)   mode 1: C[M,K] = A[M,N] B[N,K]   mode 2: C[N,K] (+)= A[M,N]^T B[M,K] */
 MDTB200_API int mdtb200_op_gemm(int mode, const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
                                 int accumulate, void* stream);
+/* the same products on tcgen05 (split-bf16 "bf16x3", fp32 accumulate): `scratch` = bf16 workspace of
+ * mdtb200_op_gemm_tc_scratch(...) ELEMENTS; needs reduce / output-column dims that are multiples of 64 (else EUNSUPPORTED) */
+MDTB200_API int64_t mdtb200_op_gemm_tc_scratch(int mode, int M, int N, int K);
+MDTB200_API int mdtb200_op_gemm_tc(int mode, const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                                   void* scratch, void* stream);
 MDTB200_API int mdtb200_op_group_sum(const float* src, float* out, int G, int T, int C, int accumulate, void* stream);
 MDTB200_API int mdtb200_op_colsum(const float* src, float* out, float* scratch, int M, int C, int accumulate, void* stream);
 /* dy == NULL: out = act(x); else out = dy * act'(x).  act: 1 GELU(erf), 2 Mish, 3 SiLU */

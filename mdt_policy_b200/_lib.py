@@ -21,7 +21,7 @@ EXPORTS = [
     "mdtb200_bind_weight", "mdtb200_commit_weights", "mdtb200_encode", "mdtb200_set_context",
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
     "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time",
-    "mdtb200_op_gemm", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
+    "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
     "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout",
 ]
 
@@ -72,6 +72,10 @@ def _declare(lib):
     lib.mdtb200_debug_gemm_time.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_float), vp]
     lib.mdtb200_debug_gemm_time.restype = i32
     lib.mdtb200_op_gemm.argtypes = [i32, fp, fp, fp, fp, i32, i32, i32, i32, vp]
+    lib.mdtb200_op_gemm_tc.argtypes = [i32, fp, fp, fp, fp, i32, i32, i32, vp, vp]
+    lib.mdtb200_op_gemm_tc.restype = i32
+    lib.mdtb200_op_gemm_tc_scratch.argtypes = [i32, i32, i32, i32]
+    lib.mdtb200_op_gemm_tc_scratch.restype = i64
     lib.mdtb200_op_group_sum.argtypes = [fp, fp, i32, i32, i32, i32, vp]
     lib.mdtb200_op_colsum.argtypes = [fp, fp, fp, i32, i32, i32, vp]
     lib.mdtb200_op_act.argtypes = [fp, fp, fp, i64, i32, vp]

@@ -177,6 +177,28 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
   dx[i] = dy[i] * d;
 }
 
+// fp32 [R, C] -> split-bf16 TRANSPOSED [C, 2*Rp] (hi | lo at column offset Rp), rows R..Rp zero-filled: turns the
+// "reduce over rows" operands of dgrad (W^T) and wgrad (dy^T, x^T) into the K-major layout of the tensor-core GEMM.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int Rp) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? src[(size_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < Rp) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[tx][i], hi, lo);
+      dst[(size_t)c * 2 * Rp + r] = hi;
+      dst[(size_t)c * 2 * Rp + Rp + r] = lo;
+    }
+  }
+}
+
 // inverted dropout with a regenerable mask: out = x * [u(seed, i) >= p] / (1 - p)   (forward on x, backward on dy)
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long n, float p, unsigned long long seed) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -23,6 +23,22 @@ int op_check(const char* what) {
 }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// process-wide TMA descriptor encoder / kernel configuration for the handle-less tensor-core ops
+tc::TmaEncoder g_op_tma;
+bool g_op_tc_ready = false;
+const char* op_tc_init() {
+  if (g_op_tc_ready) return nullptr;
+  cudaDeviceProp prop{};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) return "tensor-core ops need an sm_100 device";
+  if (const char* e = g_op_tma.init()) return e;
+  if (const char* e = tc::configure_kernels()) return e;
+  g_op_tc_ready = true;
+  return nullptr;
+}
+
 }  // namespace
 
 extern "C" {
@@ -64,6 +80,54 @@ MDTB200_API int mdtb200_op_gemm(int mode, const float* A, const float* B, const 
   const long tot = (long)n.I * n.J;
   naive_gemm_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(n);
   return op_check("naive_gemm_kernel");
+}
+
+// Same three products on the tcgen05 tensor cores with split-bf16 (bf16x3) operands; fp32 in, fp32 out.
+//   scratch: bf16 workspace of mdtb200_op_gemm_tc_scratch(mode, M, N, K) elements (operand copies in K-major hi|lo form:
+//   forward splits x and W; dgrad splits dy and W^T; wgrad splits dy^T and x^T with the row count padded to 64).
+// Requirements: reduce dim and output column count multiples of 64 (else MDTB200_EUNSUPPORTED: use mdtb200_op_gemm).
+MDTB200_API int64_t mdtb200_op_gemm_tc_scratch(int mode, int M, int N, int K) {
+  const int64_t Mp = (M + 127) / 128 * 128, M64 = (M + 63) / 64 * 64, Np = (N + 127) / 128 * 128;
+  if (mode == 0) return Mp * 2 * K + (int64_t)N * 2 * K;
+  if (mode == 1) return Mp * 2 * N + (int64_t)K * 2 * N;
+  return Np * 2 * M64 + (int64_t)K * 2 * M64;
+}
+
+MDTB200_API int mdtb200_op_gemm_tc(int mode, const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                                   void* scratch, void* stream) {
+  if (!A || !B || !C || !scratch || M < 1 || N < 1 || K < 1 || mode < 0 || mode > 2) return op_fail(MDTB200_EINVAL, "op_gemm_tc: bad argument");
+  if (const char* e = op_tc_init()) return op_fail(MDTB200_ECUDA, "op_gemm_tc: %s", e);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* s16 = reinterpret_cast<__nv_bfloat16*>(scratch);
+  tc::TcGemm t{};
+  t.bias = bias; t.C = C; t.rows_per_group = 1; t.epi = EPI_NONE; t.passes = 3;
+  const int64_t Mp = (M + 127) / 128 * 128;
+  if (mode == 0) {          // y[M,N] = x[M,K] W[N,K]^T
+    if (K % 64 || N % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm_tc: forward needs K, N multiples of 64");
+    __nv_bfloat16 *a16 = s16, *w16 = s16 + Mp * 2 * K;
+    split_weights_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, a16, M, K);
+    split_weights_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(B, w16, N, K);
+    t.A16 = a16; t.lda16 = 2 * K; t.W16 = w16; t.ldc = N; t.M = M; t.N = N; t.K = K;
+  } else if (mode == 1) {   // dx[M,K] = dy[M,N] W[N,K] = dy . (W^T)[K,N]^T
+    if (N % 64 || K % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm_tc: dgrad needs N, K multiples of 64");
+    __nv_bfloat16 *a16 = s16, *w16 = s16 + Mp * 2 * N;
+    split_weights_kernel<<<(unsigned)(((size_t)M * N + 255) / 256), 256, 0, st>>>(A, a16, M, N);
+    split_transpose_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), 256, 0, st>>>(B, w16, N, K, N);     // W [N,K] -> [K, 2N]
+    t.A16 = a16; t.lda16 = 2 * N; t.W16 = w16; t.ldc = K; t.M = M; t.N = K; t.K = N;
+  } else {                  // dW[N,K] = dy[M,N]^T x[M,K] = (dy^T)[N,M] . (x^T)[K,M]^T, reduce dim M padded to 64
+    if (K % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm_tc: wgrad needs K multiple of 64");
+    const int M64 = (M + 63) / 64 * 64;
+    const int64_t Np = (N + 127) / 128 * 128;
+    __nv_bfloat16 *a16 = s16, *w16 = s16 + Np * 2 * M64;
+    split_transpose_kernel<<<dim3((N + 31) / 32, (M64 + 31) / 32), 256, 0, st>>>(A, a16, M, N, M64);   // dy [M,N] -> [N, 2*M64]
+    split_transpose_kernel<<<dim3((K + 31) / 32, (M64 + 31) / 32), 256, 0, st>>>(B, w16, M, K, M64);   // x  [M,K] -> [K, 2*M64]
+    t.A16 = a16; t.lda16 = 2 * M64; t.W16 = w16; t.ldc = K; t.M = N; t.N = K; t.K = M64;
+  }
+  if (g_op_tma.cache.size() > 2048) g_op_tma.cache.clear();
+  // launch_tc_gemm derives the W map's leading dimension from K: W16 is always [rows, 2K] contiguous here
+  const char* e = tc::launch_tc_gemm(g_op_tma, t, st);
+  if (e) return op_fail(MDTB200_ECUDA, "op_gemm_tc: %s", e);
+  return op_check("tc_gemm_kernel (op)");
 }
 
 // out[g, c] (+)= sum_t src[g*T + t, c]

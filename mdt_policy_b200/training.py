@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 from torch.autograd import Function
@@ -21,6 +22,21 @@ from torch.autograd import Function
 from . import _lib
 
 ACT_GELU, ACT_MISH, ACT_SILU = 1, 2, 3
+
+# Linear layers (forward, input gradient, weight gradient) run on the tcgen05 tensor cores with split-bf16 ("bf16x3") operands
+# whenever the shapes allow it (reduce and output-column dims multiples of 64); MDTB200_TRAIN_TC=0 forces the exact-fp32
+# CUDA-core GEMMs everywhere (the 7-wide action embedding / output head always use them).
+USE_TC = os.environ.get("MDTB200_TRAIN_TC", "1") != "0"
+
+
+def _gemm(mode, A, B, bias, Cout, M, N, K):
+    lib = _lib.load()
+    ok = USE_TC and K % 64 == 0 and ((mode == 0 and N % 64 == 0) or (mode == 1 and N % 64 == 0) or mode == 2) and M * N * K >= (1 << 22)
+    if ok:
+        scratch = torch.empty(lib.mdtb200_op_gemm_tc_scratch(mode, M, N, K), dtype=torch.bfloat16, device=A.device)
+        _chk(lib.mdtb200_op_gemm_tc(mode, _p(A), _p(B), _p(bias), _p(Cout), M, N, K, _p(scratch), _stream(A)), "op_gemm_tc")
+    else:
+        _chk(lib.mdtb200_op_gemm(mode, _p(A), _p(B), _p(bias), _p(Cout), M, N, K, 0, _stream(A)), "op_gemm")
 
 
 def _p(t):
@@ -69,7 +85,7 @@ class Linear(Function):
         K, N = w.shape[1], w.shape[0]
         x2 = _c(x).reshape(-1, K)
         y = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
-        _chk(_lib.load().mdtb200_op_gemm(0, _p(x2), _p(w), _p(b), _p(y), x2.shape[0], N, K, 0, _stream(x)), "op_gemm fwd")
+        _gemm(0, x2, w, b, y, x2.shape[0], N, K)
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.xshape = x.shape
@@ -85,11 +101,11 @@ class Linear(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
-            _chk(lib.mdtb200_op_gemm(1, _p(dy2), _p(w), None, _p(dx), M, N, K, 0, _stream(dy)), "op_gemm dgrad")
+            _gemm(1, dy2, w, None, dx, M, N, K)
             dx = dx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
-            _chk(lib.mdtb200_op_gemm(2, _p(dy2), _p(x2), None, _p(dw), M, N, K, 0, _stream(dy)), "op_gemm wgrad")
+            _gemm(2, dy2, x2, None, dw, M, N, K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _colsum(dy2)
         return dx, dw, db

@@ -18,8 +18,13 @@ def _rel(a, b):
     return float((a.double().cpu() - b.double().cpu()).abs().max() / (b.double().abs().max() + 1e-30))
 
 
-@pytest.mark.parametrize("M,N,K", [(5120, 384, 384), (100, 1536, 384), (37, 384, 1536), (640, 7, 384), (640, 384, 7), (30, 2304, 384)])
-def test_linear_fwd_bwd(M, N, K):
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("M,N,K", [(5120, 384, 384), (100, 1536, 384), (37, 384, 1536), (640, 7, 384), (640, 384, 7), (30, 2304, 384),
+                                   (5120, 1536, 384), (1000, 384, 1536)])
+def test_linear_fwd_bwd(M, N, K, tc, monkeypatch):
+    """forward / input gradient / weight gradient in both GEMM back ends: tcgen05 bf16x3 (2^-17 operand rounding) and exact fp32"""
+    monkeypatch.setattr(T, "USE_TC", tc)
+    tol = 4e-5 if tc else 5e-6
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).double().requires_grad_()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).double().requires_grad_()
@@ -30,7 +35,7 @@ def test_linear_fwd_bwd(M, N, K):
     xc, wc, bc = (t.detach().float().cuda().requires_grad_() for t in (x, w, b))
     yc = T.Linear.apply(xc, wc, bc)
     yc.backward(dy.float().cuda())
-    assert _rel(yc, y) < 2e-6 and _rel(xc.grad, x.grad) < 2e-6 and _rel(wc.grad, w.grad) < 5e-6 and _rel(bc.grad, b.grad) < 5e-6
+    assert _rel(yc, y) < tol and _rel(xc.grad, x.grad) < tol and _rel(wc.grad, w.grad) < tol and _rel(bc.grad, b.grad) < 5e-6
 
 
 @pytest.mark.parametrize("kind,fn", [(1, torch.nn.functional.gelu), (2, torch.nn.functional.mish), (3, torch.nn.functional.silu)])
