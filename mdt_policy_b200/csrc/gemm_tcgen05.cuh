@@ -455,12 +455,11 @@ inline void launch_one(const CUtensorMap& a, const CUtensorMap& w, const TcParam
 inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t st) {
   if (g.K % BK != 0 || g.N % 64 != 0 || g.M < 1) return "unsupported GEMM shape (need K % 64 == 0, N % 64 == 0)";
   if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE) return "unsupported epilogue";
-  // tile-N choice: 128 columns when that still yields >= ~1 wave of CTAs on 148 SMs, else 64
+  // tile-N choice (measured, profiles/r01_experiments.md): 128 columns for the wide GEMMs (N >= 1024), 64 for N = d; the
+  // 192-column tile turns the fused QKV (N = 1152) into a single wave when a full batch is launched at once (mt >= 16).
+  // A "widest tile that still fills ~1 wave, else narrowest" policy was 11 % slower end to end and no better for training.
   const int mt = (g.M + BM - 1) / BM;
-  // tile width: one wave of CTAs where possible.  N = 1152 (fused QKV): 6 x 192 -> 120 CTAs at M = 2560 instead of 180 x 128
-  static const bool allow192 = !(getenv("MDTB200_NO_BN192"));
-  // (only worth it for a full-batch launch: at the M = 640 of a 4-branch graph the fatter tile just lengthens the latency chain)
-  const bool wide = allow192 && mt >= 16 && g.N % 192 == 0 && (g.N / 192) * mt <= 148 && (g.N % 128 != 0 || (g.N / 128) * mt > 148);
+  const bool wide = mt >= 16 && g.N % 192 == 0 && (g.N / 192) * mt <= 148 && (g.N % 128 != 0 || (g.N / 128) * mt > 148);
   const int bn = wide ? 192 : (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
   CUtensorMap ta, tw;
   const char* e;
