@@ -691,7 +691,7 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   if (cfg->variant != MDTB200_VARIANT_MDTV && cfg->variant != MDTB200_VARIANT_MDT) return fail(nullptr, MDTB200_EINVAL, "unknown variant %d", cfg->variant);
   if (cfg->variant == MDTB200_VARIANT_MDT && cfg->n_state_tokens != 2) return fail(nullptr, MDTB200_EINVAL, "MDT variant has exactly 2 state tokens");
   if (cfg->goal_dim % 16 || cfg->obs_dim % 16) return fail(nullptr, MDTB200_EUNSUPPORTED, "goal_dim/obs_dim must be multiples of 16");
-  if (cfg->action_dim < 1 || cfg->action_dim > 64) return fail(nullptr, MDTB200_EINVAL, "action_dim %d", cfg->action_dim);
+  if (cfg->action_dim < 1 || cfg->action_dim > 32) return fail(nullptr, MDTB200_EINVAL, "action_dim %d", cfg->action_dim);
   if (cfg->n_enc_layers < 0 || cfg->n_dec_layers < 1 || cfg->max_batch < 1) return fail(nullptr, MDTB200_EINVAL, "bad layer count / max_batch");
   if (cfg->precision < MDTB200_PREC_FP32 || cfg->precision > MDTB200_PREC_BF16) return fail(nullptr, MDTB200_EINVAL, "unknown precision %d", cfg->precision);
   if (!(cfg->sigma_data > 0.f)) return fail(nullptr, MDTB200_EINVAL, "sigma_data must be > 0");

@@ -259,13 +259,21 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const float* xr = a.x + (size_t)warp * a.d;
-  float4 v[VPL];
-  float s = 0.f;
+  const size_t mrow = (size_t)(warp / a.rows_per_group) * a.mod_stride;
+  // every global operand is requested up front (one L2 round trip instead of two dependent ones)
+  float4 v[VPL], w[VPL], bb[VPL], sh[VPL], sc[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const int c = (i * 32 + lane) * 4;
+    v[i] = *reinterpret_cast<const float4*>(xr + c);
+    w[i] = *reinterpret_cast<const float4*>(a.w + c);
+    bb[i] = a.b ? *reinterpret_cast<const float4*>(a.b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sh[i] = a.shift ? *reinterpret_cast<const float4*>(a.shift + mrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[i] = a.shift ? *reinterpret_cast<const float4*>(a.scale + mrow + c) : make_float4(1.f, 1.f, 1.f, 1.f);
   }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / (float)a.d;
   float q = 0.f;
 #pragma unroll
@@ -274,20 +282,13 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
     q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)a.d + 1e-5f);
-  const size_t mrow = (size_t)(warp / a.rows_per_group) * a.mod_stride;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = (i * 32 + lane) * 4;
-    float4 w = *reinterpret_cast<const float4*>(a.w + c);
-    float o[4] = {(v[i].x - mean) * rstd * w.x, (v[i].y - mean) * rstd * w.y, (v[i].z - mean) * rstd * w.z, (v[i].w - mean) * rstd * w.w};
-    if (a.b) {
-      float4 bb = *reinterpret_cast<const float4*>(a.b + c);
-      o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
-    }
+    float o[4] = {(v[i].x - mean) * rstd * w[i].x, (v[i].y - mean) * rstd * w[i].y, (v[i].z - mean) * rstd * w[i].z, (v[i].w - mean) * rstd * w[i].w};
+    if (a.b) { o[0] += bb[i].x; o[1] += bb[i].y; o[2] += bb[i].z; o[3] += bb[i].w; }
     if (a.shift) {
-      float4 sh = *reinterpret_cast<const float4*>(a.shift + mrow + c);
-      float4 sc = *reinterpret_cast<const float4*>(a.scale + mrow + c);
-      o[0] = sh.x + o[0] * sc.x; o[1] = sh.y + o[1] * sc.y; o[2] = sh.z + o[2] * sc.z; o[3] = sh.w + o[3] * sc.w;
+      o[0] = sh[i].x + o[0] * sc[i].x; o[1] = sh[i].y + o[1] * sc[i].y; o[2] = sh[i].z + o[2] * sc[i].z; o[3] = sh[i].w + o[3] * sc[i].w;
     }
     if (a.out) *reinterpret_cast<float4*>(a.out + (size_t)warp * a.d + c) = make_float4(o[0], o[1], o[2], o[3]);
     if (a.out16) {
@@ -600,6 +601,9 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   float c_skip = 0.f, c_out = 1.f, c_in;
   if (a.mode != HEAD_RAW) edm_scalings(sig, a.sigma_data, c_skip, c_out, c_in);
 
+  // all A dot products first (independent loads in flight together), every lane ends up with all sums ...
+  float pj[1] = {0.f};
+#pragma unroll 1
   for (int j = 0; j < a.A; ++j) {
     const float* wr = a.W + (size_t)j * a.d;
     float p = 0.f;
@@ -609,47 +613,50 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       p += (v[i].x * w.x + v[i].y * w.y) + (v[i].z * w.z + v[i].w * w.w);
     }
     p = warp_sum(p);
-    if (lane == 0) {
-      const size_t e = (size_t)warp * a.A + j;
-      float raw = p + a.bias[j];
-      if (a.mode == HEAD_RAW) { a.out[e] = raw; continue; }
-      float xin = a.x_in[e];
-      float D = raw * c_out + xin * c_skip;
-      switch (a.mode) {
-        case HEAD_DENOISE: a.out[e] = D; break;
-        case HEAD_DDIM: {
-          float t = -logf(sig), tn = -logf(sig_next), h = tn - t;
-          a.x_state[e] = (expf(-tn) / expf(-t)) * xin - expm1f(-h) * D;
-        } break;
-        case HEAD_EULER: {
-          float dd = (xin - D) / sig;
-          a.x_state[e] = xin + dd * (sig_next - sig);
-        } break;
-        case HEAD_HEUN1: {
-          float dd = (xin - D) / sig, dt = sig_next - sig;
-          if (sig_next == 0.f) { a.x_state[e] = xin + dd * dt; }
-          else { a.dbuf[e] = dd; a.x_aux[e] = xin + dd * dt; }
-        } break;
-        case HEAD_HEUN2: {   // sig = sigma_{i+1}; x_in = x2; x_state still holds x
-          float s0 = a.sigmas[a.step], dt = sig - s0;
-          float d2 = (xin - D) / sig;
-          float dp = (a.dbuf[e] + d2) / 2.0f;
-          a.x_state[e] = a.x_state[e] + dp * dt;
-        } break;
-        case HEAD_DPMPP2M: {
-          float t = -logf(sig), tn = -logf(sig_next), h = tn - t;
-          float ratio = expf(-tn) / expf(-t), em = expm1f(-h);
-          float den = D;
-          if (a.step > 0 && sig_next != 0.f) {
-            float h_last = t - (-logf(a.sigmas[a.step - 1]));
-            float r = h_last / h;
-            den = (1.0f + 1.0f / (2.0f * r)) * D - (1.0f / (2.0f * r)) * a.dbuf[e];
-          }
-          a.x_state[e] = ratio * xin - em * den;
-          a.dbuf[e] = D;
-        } break;
-        default: break;
-      }
+    if (lane == j) pj[0] = p;          // lane j keeps output j
+  }
+  // ... then lane j finishes output j: the A sampler updates run in parallel lanes instead of serially on lane 0
+  if (lane < a.A) {
+    const int j = lane;
+    const size_t e = (size_t)warp * a.A + j;
+    const float raw = pj[0] + a.bias[j];
+    if (a.mode == HEAD_RAW) { a.out[e] = raw; return; }
+    const float xin = a.x_in[e];
+    const float D = raw * c_out + xin * c_skip;
+    switch (a.mode) {
+      case HEAD_DENOISE: a.out[e] = D; break;
+      case HEAD_DDIM: {
+        float t = -logf(sig), tn = -logf(sig_next), h = tn - t;
+        a.x_state[e] = (expf(-tn) / expf(-t)) * xin - expm1f(-h) * D;
+      } break;
+      case HEAD_EULER: {
+        float dd = (xin - D) / sig;
+        a.x_state[e] = xin + dd * (sig_next - sig);
+      } break;
+      case HEAD_HEUN1: {
+        float dd = (xin - D) / sig, dt = sig_next - sig;
+        if (sig_next == 0.f) { a.x_state[e] = xin + dd * dt; }
+        else { a.dbuf[e] = dd; a.x_aux[e] = xin + dd * dt; }
+      } break;
+      case HEAD_HEUN2: {   // sig = sigma_{i+1}; x_in = x2; x_state still holds x
+        float s0 = a.sigmas[a.step], dt = sig - s0;
+        float d2 = (xin - D) / sig;
+        float dp = (a.dbuf[e] + d2) / 2.0f;
+        a.x_state[e] = a.x_state[e] + dp * dt;
+      } break;
+      case HEAD_DPMPP2M: {
+        float t = -logf(sig), tn = -logf(sig_next), h = tn - t;
+        float ratio = expf(-tn) / expf(-t), em = expm1f(-h);
+        float den = D;
+        if (a.step > 0 && sig_next != 0.f) {
+          float h_last = t - (-logf(a.sigmas[a.step - 1]));
+          float r = h_last / h;
+          den = (1.0f + 1.0f / (2.0f * r)) * D - (1.0f / (2.0f * r)) * a.dbuf[e];
+        }
+        a.x_state[e] = ratio * xin - em * den;
+        a.dbuf[e] = D;
+      } break;
+      default: break;
     }
   }
 }
