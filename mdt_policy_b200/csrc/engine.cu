@@ -62,7 +62,7 @@ struct GraphKey {
     return modality < o.modality;
   }
 };
-struct GraphEntry { cudaGraphExec_t exec; int64_t kernels; };
+struct GraphEntry { cudaGraphExec_t exec; cudaGraphExec_t exec2; int64_t kernels; };   // exec2: optional second segment
 
 }  // namespace
 
@@ -451,10 +451,10 @@ int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mo
 }
 
 // sampler iterations of one branch (sub-batch) on its own stream
-int sample_steps(MdtHandle* h, const Work& k, int sampler, int n_steps, int modality, int B, cudaStream_t st) {
-  TRY(encoder(h, k, k.in_goal, k.in_state, modality, B, st));
+int sample_steps(MdtHandle* h, const Work& k, int sampler, int n_steps, int modality, int B, cudaStream_t st, int step_begin, int step_end) {
+  if (step_begin == 0) TRY(encoder(h, k, k.in_goal, k.in_state, modality, B, st));
   const size_t mrow = (size_t)h->Ld * 6 * h->d;
-  for (int i = 0; i < n_steps; ++i) {
+  for (int i = step_begin; i < step_end; ++i) {
     HeadArgs hd{};
     hd.x_in = k.x; hd.x_state = k.x; hd.x_aux = k.x2; hd.dbuf = k.dbuf; hd.sigmas = h->sigmas; hd.step = i; hd.n_steps = n_steps;
     switch (sampler) {
@@ -478,18 +478,22 @@ int sample_steps(MdtHandle* h, const Work& k, int sampler, int n_steps, int moda
 // table of all steps is computed once; then the batch is cut into `branches` independent sub-batches whose kernel
 // chains run concurrently (fork/join through events -> parallel branches of the captured graph): every kernel of this
 // path is latency- rather than throughput-bound at B=256, so concurrent chains fill the SMs the others leave idle.
-int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cudaStream_t st) {
-  TRY(sigma_path(h, h->sigmas, n_steps, st));   // one AdaLN row per step: sigma is shared by the batch
+//
+// A call is captured as up to two graphs, [encoder + sampler steps 0..s0) and [steps s0..N): launching a ~2000-node graph costs
+// ~0.35 ms of host time before the GPU starts, so the short first segment gets the GPU going and the long second one is
+// launched while it runs (matters for the end-to-end path, where every call starts on an idle GPU).
+int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cudaStream_t st, int step_begin, int step_end) {
+  if (step_begin == 0) TRY(sigma_path(h, h->sigmas, n_steps, st));   // one AdaLN row per step: sigma is shared by the batch
   const int nb = branch_count(h, B);
   const Work base = h->work();
-  if (nb <= 1) return sample_steps(h, base, sampler, n_steps, modality, B, st);
+  if (nb <= 1) return sample_steps(h, base, sampler, n_steps, modality, B, st, step_begin, step_end);
   CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
   int rc = 0;
   for (int s = 0; s < nb && !rc; ++s) {
     const int b0 = (int)((long long)B * s / nb), b1 = (int)((long long)B * (s + 1) / nb);
     cudaStream_t bs = h->branch_streams[s];
     CUDA_TRY(h, cudaStreamWaitEvent(bs, h->ev_fork, 0));
-    rc = sample_steps(h, h->slice(base, b0), sampler, n_steps, modality, b1 - b0, bs);
+    rc = sample_steps(h, h->slice(base, b0), sampler, n_steps, modality, b1 - b0, bs, step_begin, step_end);
     CUDA_TRY(h, cudaEventRecord(h->ev_join[s], bs));
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[s], 0));
   }
@@ -755,7 +759,7 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
 
 MDTB200_API void mdtb200_destroy(MdtHandle* h) {
   if (!h) return;
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.exec2) cudaGraphExecDestroy(kv.second.exec2); }
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int i = 0; i < MdtHandle::MAX_BRANCHES; ++i) {
     if (h->branch_streams[i]) cudaStreamDestroy(h->branch_streams[i]);
@@ -779,7 +783,7 @@ MDTB200_API int mdtb200_commit_weights(MdtHandle* h, void* stream) {
   h->committed = false;
   h->ctx_B = 0;
   // cached graphs reference arena addresses: drop them, the layout may change with the set of bound tensors
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.exec2) cudaGraphExecDestroy(kv.second.exec2); }
   h->graphs.clear();
   int rc = pack_weights(h, st);
   h->bound.clear();   // source pointers are not retained
@@ -826,23 +830,35 @@ MDTB200_API int mdtb200_denoise(MdtHandle* h, const float* x, const float* sigma
   return decoder_eval(h, h->work(), x, h->mod, h->Ld * 6 * h->d, sigma, 1, precondition, B, hd, st);
 }
 
-static int get_graph(MdtHandle* h, int sampler, int n_steps, int modality, int B, GraphEntry** out) {
-  GraphKey key{B, n_steps, sampler, modality};
-  auto it = h->graphs.find(key);
-  if (it != h->graphs.end()) { *out = &it->second; return 0; }
+static int capture_segment(MdtHandle* h, int sampler, int n_steps, int modality, int B, int step_begin, int step_end, cudaGraphExec_t* exec) {
   cudaGraph_t graph = nullptr;
   CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  h->capturing = true; h->capture_count = 0;
-  int rc = sample_body(h, sampler, n_steps, modality, B, h->cap_stream);
+  h->capturing = true;
+  int rc = sample_body(h, sampler, n_steps, modality, B, h->cap_stream, step_begin, step_end);
   h->capturing = false;
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
-  GraphEntry ge{};
-  ge.kernels = h->capture_count;
-  e = cudaGraphInstantiate(&ge.exec, graph, 0);
+  e = cudaGraphInstantiate(exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) return fail(h, MDTB200_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int get_graph(MdtHandle* h, int sampler, int n_steps, int modality, int B, GraphEntry** out) {
+  GraphKey key{B, n_steps, sampler, modality};
+  auto it = h->graphs.find(key);
+  if (it != h->graphs.end()) { *out = &it->second; return 0; }
+  GraphEntry ge{};
+  h->capture_count = 0;
+  static const bool split = !getenv("MDTB200_SINGLE_GRAPH");
+  const int s0 = (split && n_steps > 3) ? 2 : n_steps;
+  TRY(capture_segment(h, sampler, n_steps, modality, B, 0, s0, &ge.exec));
+  if (s0 < n_steps) {
+    int rc = capture_segment(h, sampler, n_steps, modality, B, s0, n_steps, &ge.exec2);
+    if (rc) { cudaGraphExecDestroy(ge.exec); return rc; }
+  }
+  ge.kernels = h->capture_count;
   auto ins = h->graphs.emplace(key, ge);
   *out = &ins.first->second;
   return 0;
@@ -867,6 +883,7 @@ static int sample_impl(MdtHandle* h, int sampler, const float* sigmas, int n_ste
   CUDA_TRY(h, cudaMemcpyAsync(h->in_state, state, (size_t)B * h->Ts * h->cfg.obs_dim * 4, in_kind, st));
   CUDA_TRY(h, cudaMemcpyAsync(h->x, x_inout, xb, in_kind, st));
   CUDA_TRY(h, cudaGraphLaunch(ge->exec, st));
+  if (ge->exec2) CUDA_TRY(h, cudaGraphLaunch(ge->exec2, st));
   h->launches += ge->kernels;
   h->ctx_B = B;
   CUDA_TRY(h, cudaMemcpyAsync(x_inout, h->x, xb, out_kind, st));

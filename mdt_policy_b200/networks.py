@@ -169,9 +169,19 @@ class _Engine:
                 if id(d[leaf]) not in seen:
                     seen.add(id(d[leaf])); uniq.append((full, d, leaf))
             slots = self._slots = uniq
+        # cheap per-call check first (the e2e path pays for every microsecond here): identity and version counters of the live
+        # Parameter objects; storage moves (.to(), .cuda()) mark the module dirty through _ScoreNetBase._apply
+        quick = 0
+        for _, d, leaf in slots:
+            p = d[leaf]
+            quick += id(p) + p._version
+        if quick == self.__dict__.get("_quick_key") and not owner.__dict__.get("_weights_dirty", True):
+            return
         params = [(full, d[leaf]) for full, d, leaf in slots]
         key = tuple([(p.data_ptr(), p._version) for _, p in params])
         if key == self.weights_key:
+            self._quick_key = quick
+            owner.__dict__["_weights_dirty"] = False
             return
         for name, p in params:
             if p.device != self.device:
@@ -182,6 +192,8 @@ class _Engine:
             self.check(self.lib.mdtb200_bind_weight(self.handle, (prefix + name).encode(), _ptr(t), t.numel()), "bind_weight")
         self.check(self.lib.mdtb200_commit_weights(self.handle, self.stream), "commit_weights")
         self.weights_key = key
+        self._quick_key = quick
+        owner.__dict__["_weights_dirty"] = False
 
     def launch_count(self) -> int:
         return int(self.lib.mdtb200_launch_count(self.handle))
@@ -272,9 +284,15 @@ class _ScoreNetBase(nn.Module):
         lang = self.use_modality_encoder and "modality" in states and states["modality"] == "lang"
         return _lib.MODALITY_LANG if lang else _lib.MODALITY_VIS
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() may move parameter storage without touching version counters: force a full weight check
+        self.__dict__["_weights_dirty"] = True
+        return super()._apply(fn, *args, **kwargs)
+
     def _check_mode(self):
-        if self.training and (self.cond_mask_prob > 0 or any(
-                isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules())):
+        if not self.training:
+            return
+        if self.cond_mask_prob > 0 or any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules()):
             raise NotImplementedError(
                 "train-mode forward under torch.no_grad(): the inference kernels implement eval semantics only (no dropout / goal "
                 "masking); call .eval(), or enable autograd to run the training path (mdt_policy_b200/training.py)")
