@@ -388,26 +388,34 @@ def main():
                      "kernel": "whole sampling graph (encode + 10 steps), algorithmic FLOPs ALG(B,N) of SURVEY 8d",
                      "alg_gflop_per_launch": flops / 1e9, "peak_source": peak_src},
     }
-    # dominant kernel (tcgen05 GEMM, 69 % of kernel time): live CUDA-event timing of back-to-back launches per decoder shape
+    # Dominant kernel = tc::tc_gemm_kernel (72 % of kernel time, profiles/r01_v7_summary.md).  Kernels inside a CUDA graph cannot be
+    # bracketed by events one by one, so each decoder GEMM shape is timed live here with CUDA events over 200 back-to-back launches
+    # (mdtb200_debug_gemm_time, L2-warm, same kernel/instantiation the graph uses at M = B*10) and weighted by its launch count per
+    # decoder layer.  The whole-graph figure (all kernels, ALG(B,N) of SURVEY 8d over the timed calls) is kept as `whole_graph`.
+    whole = line["roofline"]
     if args.precision != "fp32":
         try:
             eng = list(model.inner_model._engines.values())[0]
             M, d = B * 10, 384
-            shapes = {"qkv (N=3d,K=d)": (M, 3 * d, d, 0), "attn/cross c_proj, cross q (N=d,K=d, +res)": (M, d, d, 4),
-                      "mlp c_fc + GELU (N=4d,K=d)": (M, 4 * d, d, 1), "mlp c_proj + gate + res (N=d,K=4d)": (M, d, 4 * d, 5)}
-            per = {}
-            for name, (m, n, k, epi) in shapes.items():
+            shapes = {"qkv (N=3d,K=d)": (M, 3 * d, d, 0, 1), "attn/cross c_proj, cross q (N=d,K=d,+res)": (M, d, d, 4, 3),
+                      "mlp c_fc + GELU (N=4d,K=d)": (M, 4 * d, d, 1, 1), "mlp c_proj + gate + res (N=d,K=4d)": (M, d, 4 * d, 5, 1)}
+            per, tot_flop, tot_us = {}, 0.0, 0.0
+            for name, (m, n, k, epi, count) in shapes.items():
                 us = eng.gemm_time_us(m, n, k, epi, 200)
-                per[name] = {"us": us, "alg_tflops": 2.0 * m * n * k / us / 1e6, "frac": 2.0 * m * n * k / us / 1e6 / peak}
-            dom = per["mlp c_fc + GELU (N=4d,K=d)"]
-            line["roofline"]["dominant_kernel"] = {
-                "name": "tc::tc_gemm_kernel<128,3> (mlp c_fc + GELU, M=%d N=%d K=%d)" % (M, 4 * d, d), "achieved": dom["alg_tflops"],
-                "frac": dom["frac"], "us_per_launch": dom["us"], "alg_gflop_per_launch": 2.0 * M * 4 * d * d / 1e9,
-                "note": "bf16x3 issues 3x the algorithmic FLOPs: ceiling 1/3", "all_gemm_shapes": per,
-                "traffic_bytes_per_launch_ncu": 1300,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r01_v7_summary.md (working set is L2-resident)"}
+                per[name] = {"us_per_launch": us, "launches_per_layer": count, "alg_tflops": 2.0 * m * n * k / us / 1e6,
+                             "frac": 2.0 * m * n * k / us / 1e6 / peak}
+                tot_flop += 2.0 * m * n * k * count
+                tot_us += us * count
+            ach = tot_flop / tot_us / 1e6
+            line["roofline"] = {
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 1300,
+                "kernel": "tc::tc_gemm_kernel<BN,3> (tcgen05 bf16x3 GEMM), launch-weighted over the 6 GEMMs of a decoder layer at M=%d" % M,
+                "alg_gflop_per_launch": tot_flop / 6 / 1e9, "us_per_launch": tot_us / 6, "peak_source": peak_src,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_v7_summary.md): L2-resident",
+                "note": "bf16x3 issues 3x the algorithmic FLOPs, ceiling 1/3; per-SM operand ingest (~64 B/clk) is the binding limit, see DESIGN.md",
+                "shapes": per, "whole_graph": whole}
         except Exception as e:  # noqa: BLE001
-            line["roofline"]["dominant_kernel"] = {"error": repr(e)}
+            line["roofline"]["dominant_kernel_error"] = repr(e)
     if world == 1 and not args.no_cpu_baseline:
         _, desc, _ = cpu_reference_run(enc, dec, B, steps=5, warmup=2, budget_s=40.0)
         line["cpu_baseline"] = desc

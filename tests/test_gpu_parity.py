@@ -221,3 +221,25 @@ def test_agent_host_path_uncond_and_ancestral():
     torch.manual_seed(0)
     e2 = gcs.sample_euler_ancestral(model, state, inp["x_T"].cuda(), inp["goal"].cuda(), sig.cuda())
     assert torch.isfinite(e1).all() and torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize("variant,B", [("mdtv", 200), ("mdtv", 131), ("mdt", 160)])
+def test_multi_branch_ragged_fused_vs_generic(variant, B):
+    """The fused graph cuts the batch into 4 concurrent sub-batch chains (here 50 / 32-33 / 40 samples each: ragged 128-row
+    tiles, branch offsets that are not tile-aligned); it must agree with the per-step host loop (single chain, one
+    mdtb200_denoise per evaluation) for both network variants."""
+    from mdt_policy_b200 import gc_sampling as gcs
+    if variant == "mdtv":
+        model = H.build_product(H.mdtv_inner_cfg(2, 2, precision="bf16x3"), 85, "trained")
+        inp = {k: v.cuda() for k, v in synthetic_inputs(B, seed=86).items()}
+        state = {"state_images": inp["state_images"], "modality": "lang"}
+    else:
+        model = H.build_product(H.mdt_inner_cfg(n_enc_layers=2, n_dec_layers=2, precision="bf16x3"), 87, "trained")
+        inp = {k: v.cuda() for k, v in synthetic_inputs(B, seed=88, n_state_tokens=2, obs_dim=512).items()}
+        state = {"static": inp["state_images"][:, :1], "gripper": inp["state_images"][:, 1:], "modality": "vis"}
+    sig = gcs.get_sigmas_exponential(5, 0.01, 80.0, "cuda")
+    for fn in (gcs.sample_ddim, gcs.sample_heun):
+        fused = fn(model, state, inp["x_T"], inp["goal"], sig, disable=True)
+        loop = fn(model, state, inp["x_T"], inp["goal"], sig, disable=True, callback=lambda d: None)
+        assert torch.isfinite(fused).all()
+        assert (fused - loop).abs().max() < 3e-5, (fn.__name__, float((fused - loop).abs().max()))
