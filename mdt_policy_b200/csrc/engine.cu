@@ -14,6 +14,7 @@
 #include "../../include/mdtb200.h"
 #include "kernels_simt.cuh"
 #include "gemm_tcgen05.cuh"
+#include "fused_decoder.cuh"
 
 #include <cuda_runtime.h>
 #include <cstdarg>
@@ -62,7 +63,12 @@ struct GraphKey {
     return modality < o.modality;
   }
 };
-struct GraphEntry { cudaGraphExec_t exec; cudaGraphExec_t exec2; int64_t kernels; };   // exec2: optional second segment
+// device-side program of the persistent fused decoder (fused_decoder.cuh) for one (B, N, sampler) sampling call
+struct FusedPlan {
+  fd::Phase* d_prog = nullptr; fd::GemmDesc* d_gemms = nullptr; CUtensorMap* d_maps = nullptr; int n_phases = 0; int grid = 0; int n_rowgroups = 0;
+  fd::FusedParams params{};
+};
+struct GraphEntry { cudaGraphExec_t exec; cudaGraphExec_t exec2; int64_t kernels; FusedPlan* plan; uint64_t last_use; };   // exec2: optional second segment
 
 }  // namespace
 
@@ -94,8 +100,17 @@ struct MdtHandle {
   __nv_bfloat16 *a16 = nullptr, *y16 = nullptr, *h16 = nullptr;   // split-bf16 operand copies (hi | lo)
   int mod_rows = 0;
 
+  // persistent fused decoder (fused_decoder.cuh): split-K partial sums (C, Mp, d) and per-row-group progress counters
+  bool fused = false; int fd_C = 0, fd_SPG = 0, fd_groups_max = 0;
+  float* fd_partial = nullptr; int* fd_progress = nullptr; size_t fd_progress_bytes = 0;
+  unsigned long long* fd_trace = nullptr;
+  FusedPlan* cur_plan = nullptr;  // plan of the graph being captured
+  uint64_t use_clock = 0;
+  FusedPlan* denoise_plan = nullptr; int denoise_plan_B = 0, denoise_plan_pre = -1;
+
   cudaStream_t cap_stream = nullptr;
   static constexpr int MAX_BRANCHES = 8;
+  static constexpr size_t MAX_GRAPHS = 16;
   cudaStream_t branch_streams[MAX_BRANCHES] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES] = {};
   int branches = 4;               // MDTB200_BRANCHES overrides
@@ -474,6 +489,227 @@ int sample_steps(MdtHandle* h, const Work& k, int sampler, int n_steps, int moda
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ persistent fused decoder
+// One evaluation of the score network inside a fused program: which sigma row of the AdaLN table it uses, what the output
+// head does with the result and which action buffer the network reads.
+struct EvalSpec { int sig; int mode; int step; const float* x_in; };
+
+void free_plan(FusedPlan* pl) {
+  if (!pl) return;
+  if (pl->d_prog) cudaFree(pl->d_prog);
+  if (pl->d_gemms) cudaFree(pl->d_gemms);
+  if (pl->d_maps) cudaFree(pl->d_maps);
+  delete pl;
+}
+
+void drop_graph(GraphEntry& ge) {
+  if (ge.exec) cudaGraphExecDestroy(ge.exec);
+  if (ge.exec2) cudaGraphExecDestroy(ge.exec2);
+  free_plan(ge.plan);
+  ge = GraphEntry{};
+}
+
+// Builds the phase program (fused_decoder.cuh) for `evals` consecutive score evaluations on the handle's static buffers.
+//   mod / mod_stride     AdaLN table; row of evaluation e = mod + evals[e].sig * mrow (sampling: one sigma per step, shared by
+//                        the batch, mod_stride = 0) or one row per sample (denoise API: evals[0].sig = 0, mod_stride = mrow)
+//   sigma / sigma_stride the c_in scaling and the RAW / DENOISE head read sigma[evals[e].sig + sample * sigma_stride]
+int build_fused_plan(MdtHandle* h, int B, const std::vector<EvalSpec>& evals, int n_steps, const float* mod, int mod_stride,
+                     const float* sigma, int sigma_stride, int precondition, float* hout, FusedPlan** out) {
+  const int d = h->d, T = h->T, Tc = h->Tc, Ld = h->Ld, C = h->fd_C, SPG = h->fd_SPG;
+  const size_t Mp = ((size_t)h->cfg.max_batch * T + 127) / 128 * 128;
+  const Weights& w = h->w;
+  const Work k = h->work();
+  const size_t mrow = (size_t)Ld * 6 * d;
+  std::vector<CUtensorMap> maps(3 + 6 * Ld);
+  const char* e;
+  if ((e = h->tma.get(k.a16, (int)Mp, 2 * d, 2 * d, 128, &maps[0])) || (e = h->tma.get(k.y16, (int)Mp, 2 * d, 2 * d, 128, &maps[1])) ||
+      (e = h->tma.get(k.h16, (int)Mp, 8 * d, 8 * d, 128, &maps[2])))
+    return fail(h, MDTB200_ECUDA, "fused plan: %s", e);
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayerW& L = w.dec[l];
+    CUtensorMap* m = &maps[3 + 6 * l];
+    if ((e = h->tma.get(L.wqkv16, 3 * d, 2 * d, 2 * d, 192, m + 0)) || (e = h->tma.get(L.wo16, d, 2 * d, 2 * d, 64, m + 1)) ||
+        (e = h->tma.get(L.wq16, d, 2 * d, 2 * d, 64, m + 2)) || (e = h->tma.get(L.wco16, d, 2 * d, 2 * d, 64, m + 3)) ||
+        (e = h->tma.get(L.wfc16, 4 * d, 2 * d, 2 * d, 256, m + 4)) || (e = h->tma.get(L.wproj16, d, 8 * d, 8 * d, d / 2, m + 5)))
+      return fail(h, MDTB200_ECUDA, "fused plan: %s", e);
+  }
+  std::vector<fd::Phase> prog;
+  std::vector<fd::GemmDesc> gemms;
+  int acc = 0;
+  auto blank = [&](int type) {
+    fd::Phase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.type = type; ph.dep = (int)prog.size(); ph.head_mode = -1; ph.cta_mod = C;
+    return ph;
+  };
+  // GEMM phase: every CTA computes W rows / output columns [cta * bn, +bn) from the full-K operand in tensor map a_map
+  auto gemm_ph = [&](int a_map, int a_lo, int w_map, int nkb, int bn, int epi, fd::GemmDesc& g) {
+    fd::Phase ph = blank(fd::PH_GEMM);
+    ph.bn = bn; ph.epi = epi; ph.acc_buf = (acc++) & 1;
+    ph.w_row_s1 = bn; ph.o_col_s1 = bn;
+    memset(&g, 0, sizeof(g));
+    g.a_map = a_map; g.a_lo_off = a_lo; g.w_map = w_map; g.nkb = nkb; g.bn = bn; g.acc_buf = ph.acc_buf; g.cta_mod = C;
+    g.w_row_s1 = bn; g.w_lo_off = d;
+    return ph;
+  };
+  auto push_gemm = [&](fd::Phase& ph, fd::GemmDesc& g) {
+    g.p = (int)prog.size(); g.dep = ph.dep;
+    prog.push_back(ph); gemms.push_back(g);
+  };
+  auto ln_fields = [&](fd::Phase& ph, const float* lw, const float* lb, const float* shift, const float* scale) {
+    ph.ln = 1; ph.ln_w = lw; ph.ln_b = lb; ph.shift = shift; ph.scale = scale; ph.mod_stride = mod_stride;
+    ph.out16 = k.a16; ph.ldo = 2 * d; ph.lo_off16 = d;
+  };
+  const float att_scale = 1.0f / sqrtf((float)h->hd);
+  {  // action embedding of the first evaluation + LN1 / modulate of layer 0
+    fd::Phase ph = blank(fd::PH_ROW);
+    const float* m0 = mod + (size_t)evals[0].sig * mrow;
+    ph.xh = k.xh; ph.embed = 1; ph.emb_x = evals[0].x_in; ph.ae_w = w.ae_w; ph.ae_b = w.ae_b;
+    ph.emb_sigma = sigma + evals[0].sig; ph.emb_sigma_stride = sigma_stride; ph.precondition = precondition;
+    ln_fields(ph, w.dec[0].ln1_w, w.dec[0].ln1_b, m0, m0 + d);
+    prog.push_back(ph);
+  }
+  for (size_t ei = 0; ei < evals.size(); ++ei) {
+    const EvalSpec& ev = evals[ei];
+    const float* me = mod + (size_t)ev.sig * mrow;
+    for (int l = 0; l < Ld; ++l) {
+      const DecLayerW& L = w.dec[l];
+      const float* ml = me + (size_t)l * 6 * d;
+      const int mb = 3 + 6 * l;
+      fd::GemmDesc g;
+      {  // qkv = a . [Wq;Wk;Wv]^T + b
+        fd::Phase ph = gemm_ph(0, d, mb + 0, d / 64, 192, fd::FE_STORE, g);
+        ph.bias = L.bqkv; ph.out = k.qkv; ph.ldo = 3 * d;
+        push_gemm(ph, g);
+      }
+      {  // causal self-attention -> y16
+        fd::Phase ph = blank(fd::PH_ATTN);
+        ph.q = k.qkv; ph.k = k.qkv + d; ph.v = k.qkv + 2 * d; ph.ldq = 3 * d; ph.ldkv = 3 * d; ph.Tq = T; ph.Tk = T; ph.causal = 1; ph.att_scale = att_scale;
+        ph.out16 = k.y16; ph.ldo = 2 * d; ph.lo_off16 = d;
+        prog.push_back(ph);
+      }
+      {  // x += gate_msa * (y . Wo^T + b)
+        fd::Phase ph = gemm_ph(1, d, mb + 1, d / 64, 64, fd::FE_RESID, g);
+        ph.bias = L.bo; ph.out = k.xh; ph.ldo = d; ph.gate = ml + 2 * d; ph.gate_stride = mod_stride;
+        push_gemm(ph, g);
+      }
+      {  // LN3 -> a16
+        fd::Phase ph = blank(fd::PH_ROW);
+        ph.xh = k.xh;
+        ln_fields(ph, L.ln3_w, L.ln3_b, nullptr, nullptr);
+        prog.push_back(ph);
+      }
+      {  // q = a . Wq^T + b
+        fd::Phase ph = gemm_ph(0, d, mb + 2, d / 64, 64, fd::FE_STORE, g);
+        ph.bias = L.bq; ph.out = k.q; ph.ldo = d;
+        push_gemm(ph, g);
+      }
+      {  // cross-attention over the cached context K/V (causal top-left mask)
+        fd::Phase ph = blank(fd::PH_ATTN);
+        ph.q = k.q; ph.ldq = d; ph.k = k.kv + (size_t)l * 2 * d; ph.v = k.kv + (size_t)l * 2 * d + d; ph.ldkv = Ld * 2 * d;
+        ph.Tq = T; ph.Tk = Tc; ph.causal = 1; ph.att_scale = att_scale;
+        ph.out16 = k.y16; ph.ldo = 2 * d; ph.lo_off16 = d;
+        prog.push_back(ph);
+      }
+      {  // x += y . Wco^T + b
+        fd::Phase ph = gemm_ph(1, d, mb + 3, d / 64, 64, fd::FE_RESID, g);
+        ph.bias = L.bco; ph.out = k.xh; ph.ldo = d;
+        push_gemm(ph, g);
+      }
+      {  // LN2 + modulate -> a16
+        fd::Phase ph = blank(fd::PH_ROW);
+        ph.xh = k.xh;
+        ln_fields(ph, L.ln2_w, L.ln2_b, ml + 3 * d, ml + 4 * d);
+        prog.push_back(ph);
+      }
+      {  // h16[:, slice] = split(gelu(a . Wfc[slice]^T + b))
+        fd::Phase ph = gemm_ph(0, d, mb + 4, d / 64, 256, fd::FE_GELU16, g);
+        ph.bias = L.bfc; ph.out16 = k.h16; ph.ldo = 8 * d; ph.lo_off16 = 4 * d;
+        push_gemm(ph, g);
+      }
+      {  // c_proj as a (C/2 x 2) grid of (K slice of 512 hidden columns) x (N half): C/2 partial sums per output element
+        fd::Phase ph = gemm_ph(2, 4 * d, mb + 5, 512 / 64, d / 2, fd::FE_PARTIAL, g);
+        ph.cta_mod = C / 2; ph.w_row_s1 = 0; ph.w_row_s2 = d / 2; ph.o_col_s1 = 0; ph.o_col_s2 = d / 2;
+        ph.out = h->fd_partial; ph.out_cta_stride = (long long)Mp * d; ph.ldo = d;
+        g.cta_mod = C / 2; g.a_col_s1 = 512; g.w_row_s1 = 0; g.w_row_s2 = d / 2; g.w_col_s1 = 512; g.w_lo_off = 4 * d;
+        push_gemm(ph, g);
+      }
+      {  // x += gate_mlp * (sum of partials + b); then the next consumer's LayerNorm (or the output head)
+        fd::Phase ph = blank(fd::PH_ROW);
+        ph.xh = k.xh; ph.n_part = C / 2; ph.part = h->fd_partial; ph.part_stride = (long long)Mp * d; ph.pbias = L.bproj;
+        ph.rgate = ml + 5 * d; ph.rgate_stride = mod_stride;
+        if (l + 1 < Ld) {
+          const float* mn = me + (size_t)(l + 1) * 6 * d;
+          ln_fields(ph, w.dec[l + 1].ln1_w, w.dec[l + 1].ln1_b, mn, mn + d);
+        } else {
+          ph.head_mode = ev.mode; ph.dln_w = w.dec_ln_w; ph.dln_b = w.dec_ln_b; ph.ap_w = w.ap_w; ph.ap_b = w.ap_b;
+          ph.x_in = ev.x_in; ph.x_state = k.x; ph.x_aux = k.x2; ph.dbuf = k.dbuf; ph.hout = hout;
+          ph.sigmas = h->sigmas; ph.step = ev.step; ph.n_steps = n_steps; ph.hsigma = sigma; ph.hsigma_stride = sigma_stride;
+          if (ei + 1 < evals.size()) {
+            const EvalSpec& nx = evals[ei + 1];
+            const float* mn = mod + (size_t)nx.sig * mrow;
+            ph.embed = 1; ph.emb_x = nullptr; ph.ae_w = w.ae_w; ph.ae_b = w.ae_b;
+            ph.emb_sigma = sigma + nx.sig; ph.emb_sigma_stride = sigma_stride; ph.precondition = precondition;
+            ln_fields(ph, w.dec[0].ln1_w, w.dec[0].ln1_b, mn, mn + d);
+          }
+        }
+        prog.push_back(ph);
+      }
+    }
+  }
+  prog.push_back(blank(fd::PH_END));
+
+  FusedPlan* pl = new (std::nothrow) FusedPlan();
+  if (!pl) return fail(h, MDTB200_ENOMEM, "out of host memory");
+  pl->n_phases = (int)prog.size();
+  pl->n_rowgroups = (B + SPG - 1) / SPG;
+  const int ng = pl->n_rowgroups < h->fd_groups_max ? pl->n_rowgroups : h->fd_groups_max;
+  pl->grid = ng * C;
+  if ((size_t)pl->n_rowgroups * 32 * sizeof(int) > h->fd_progress_bytes) { free_plan(pl); return fail(h, MDTB200_EINVAL, "fused plan: too many row groups"); }
+  if (cudaMalloc(&pl->d_prog, prog.size() * sizeof(fd::Phase)) != cudaSuccess || cudaMalloc(&pl->d_maps, maps.size() * sizeof(CUtensorMap)) != cudaSuccess ||
+      cudaMalloc(&pl->d_gemms, gemms.size() * sizeof(fd::GemmDesc)) != cudaSuccess ||
+      cudaMemcpy(pl->d_gemms, gemms.data(), gemms.size() * sizeof(fd::GemmDesc), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(pl->d_prog, prog.data(), prog.size() * sizeof(fd::Phase), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(pl->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) {
+    free_plan(pl);
+    cudaGetLastError();
+    return fail(h, MDTB200_ENOMEM, "fused plan: device allocation failed");
+  }
+  fd::FusedParams& P = pl->params;
+  P.prog = pl->d_prog; P.gemms = pl->d_gemms; P.n_gemms = (int)gemms.size(); P.maps = pl->d_maps; P.progress = h->fd_progress;
+  P.B = B; P.T = T; P.A = h->A; P.d = d; P.H = h->H; P.hd = h->hd; P.C = C; P.SPG = SPG; P.n_rowgroups = pl->n_rowgroups;
+  P.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1; P.sigma_data = h->cfg.sigma_data;
+  P.trace = h->fd_trace;
+  *out = pl;
+  return 0;
+}
+
+int launch_fused(MdtHandle* h, const FusedPlan* pl, cudaStream_t st) {
+  CUDA_TRY(h, cudaMemsetAsync(h->fd_progress, 0, (size_t)pl->n_rowgroups * 32 * sizeof(int), st));
+  if (h->d == 384) fd::fused_decoder_kernel<3><<<pl->grid, fd::FD_THREADS, fd::SMEM_TOTAL, st>>>(pl->params);
+  else fd::fused_decoder_kernel<4><<<pl->grid, fd::FD_THREADS, fd::SMEM_TOTAL, st>>>(pl->params);
+  count_launch(h);
+  return check_launch(h, "fused_decoder_kernel");
+}
+
+// evaluations of a sampler run (same sequence as sample_steps)
+std::vector<EvalSpec> sampler_evals(const MdtHandle* h, int sampler, int n_steps) {
+  std::vector<EvalSpec> ev;
+  for (int i = 0; i < n_steps; ++i) {
+    int mode = HEAD_DDIM;
+    switch (sampler) {
+      case MDTB200_SAMPLER_EULER: mode = HEAD_EULER; break;
+      case MDTB200_SAMPLER_HEUN: mode = HEAD_HEUN1; break;
+      case MDTB200_SAMPLER_DPMPP_2M: mode = HEAD_DPMPP2M; break;
+      default: break;
+    }
+    ev.push_back(EvalSpec{i, mode, i, h->x});
+    if (sampler == MDTB200_SAMPLER_HEUN && i + 1 < n_steps) ev.push_back(EvalSpec{i + 1, HEAD_HEUN2, i, h->x2});
+  }
+  return ev;
+}
+
 // The whole sampling call on the handle's static buffers (captured into a graph by mdtb200_sample).  The AdaLN
 // table of all steps is computed once; then the batch is cut into `branches` independent sub-batches whose kernel
 // chains run concurrently (fork/join through events -> parallel branches of the captured graph): every kernel of this
@@ -486,18 +722,24 @@ int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cud
   if (step_begin == 0) TRY(sigma_path(h, h->sigmas, n_steps, st));   // one AdaLN row per step: sigma is shared by the batch
   const int nb = branch_count(h, B);
   const Work base = h->work();
-  if (nb <= 1) return sample_steps(h, base, sampler, n_steps, modality, B, st, step_begin, step_end);
-  CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+  const FusedPlan* plan = h->cur_plan;        // fused decoder: the branches only run the encoder, then ONE persistent kernel
+  const int enc_end = plan ? 0 : step_end;
   int rc = 0;
-  for (int s = 0; s < nb && !rc; ++s) {
-    const int b0 = (int)((long long)B * s / nb), b1 = (int)((long long)B * (s + 1) / nb);
-    cudaStream_t bs = h->branch_streams[s];
-    CUDA_TRY(h, cudaStreamWaitEvent(bs, h->ev_fork, 0));
-    rc = sample_steps(h, h->slice(base, b0), sampler, n_steps, modality, b1 - b0, bs, step_begin, step_end);
-    CUDA_TRY(h, cudaEventRecord(h->ev_join[s], bs));
-    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[s], 0));
+  if (nb <= 1) {
+    rc = sample_steps(h, base, sampler, n_steps, modality, B, st, step_begin, enc_end);
+  } else {
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    for (int s = 0; s < nb && !rc; ++s) {
+      const int b0 = (int)((long long)B * s / nb), b1 = (int)((long long)B * (s + 1) / nb);
+      cudaStream_t bs = h->branch_streams[s];
+      CUDA_TRY(h, cudaStreamWaitEvent(bs, h->ev_fork, 0));
+      rc = sample_steps(h, h->slice(base, b0), sampler, n_steps, modality, b1 - b0, bs, step_begin, enc_end);
+      CUDA_TRY(h, cudaEventRecord(h->ev_join[s], bs));
+      CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[s], 0));
+    }
   }
-  return rc;
+  if (rc || !plan) return rc;
+  return launch_fused(h, plan, st);
 }
 
 // ------------------------------------------------------------------------------------------ weights
@@ -740,6 +982,26 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
     if ((rc = dev_alloc(h, &h->a16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->y16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->h16, Mp * 8 * Dd))) return bail(rc);
     cudaMemset(h->a16, 0, Mp * 2 * Dd * 2); cudaMemset(h->y16, 0, Mp * 2 * Dd * 2); cudaMemset(h->h16, 0, Mp * 8 * Dd * 2);
   }
+  if (cfg->precision != MDTB200_PREC_FP32 && (d == 384 || d == 512) && 128 / h->T >= 1 && h->A <= 32) {
+    // persistent fused decoder: C = d / 64 CTAs per row group of SPG = 128 / T samples (fused_decoder.cuh)
+    const char* on = getenv("MDTB200_FUSED");     // opt-in: measured slower than the multi-branch graph (profiles/r02_fused_decoder.md)
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, h->device);
+    h->fd_C = d / 64; h->fd_SPG = 128 / h->T; h->fd_groups_max = prop.multiProcessorCount / h->fd_C;
+    const size_t att = (size_t)2 * (h->T + 2 * (h->T > h->Tc ? h->T : h->Tc)) * (d + 4) * 4 + (size_t)2 * h->H * h->T * (h->T + 1) * 4;
+    if (on && on[0] == '1' && h->fd_groups_max >= 1 && att <= (size_t)fd::ROW_SCR_BYTES) {
+      const char* e = fd::configure_fused();
+      if (e) { fail(h, MDTB200_ECUDA, "fused decoder configuration failed: %s", e); return bail(MDTB200_ECUDA); }
+      const size_t Mp = (M + 127) / 128 * 128;
+      h->fd_progress_bytes = ((B + h->fd_SPG - 1) / h->fd_SPG) * 32 * sizeof(int);
+      if ((rc = dev_alloc(h, &h->fd_partial, (size_t)(h->fd_C / 2) * Mp * Dd)) || (rc = dev_alloc(h, &h->fd_progress, h->fd_progress_bytes / sizeof(int)))) return bail(rc);
+      h->fused = true;
+      if (getenv("MDTB200_FUSED_TRACE")) {
+        if ((rc = dev_alloc(h, &h->fd_trace, (size_t)fd::TRACE_PHASES * 160 * 8))) return bail(rc);
+        cudaMemset(h->fd_trace, 0, (size_t)fd::TRACE_PHASES * 160 * 8 * 8);
+      }
+    }
+  }
   {
     size_t att = attention_smem_bytes(d, h->H, h->T, h->T);
     if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att) != cudaSuccess) {
@@ -759,7 +1021,8 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
 
 MDTB200_API void mdtb200_destroy(MdtHandle* h) {
   if (!h) return;
-  for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.exec2) cudaGraphExecDestroy(kv.second.exec2); }
+  for (auto& kv : h->graphs) drop_graph(kv.second);
+  free_plan(h->denoise_plan);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int i = 0; i < MdtHandle::MAX_BRANCHES; ++i) {
     if (h->branch_streams[i]) cudaStreamDestroy(h->branch_streams[i]);
@@ -783,8 +1046,10 @@ MDTB200_API int mdtb200_commit_weights(MdtHandle* h, void* stream) {
   h->committed = false;
   h->ctx_B = 0;
   // cached graphs reference arena addresses: drop them, the layout may change with the set of bound tensors
-  for (auto& kv : h->graphs) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.exec2) cudaGraphExecDestroy(kv.second.exec2); }
+  for (auto& kv : h->graphs) drop_graph(kv.second);
   h->graphs.clear();
+  free_plan(h->denoise_plan); h->denoise_plan = nullptr; h->denoise_plan_B = 0;
+  h->tma.cache.clear();
   int rc = pack_weights(h, st);
   h->bound.clear();   // source pointers are not retained
   if (rc) return rc;
@@ -848,17 +1113,29 @@ static int capture_segment(MdtHandle* h, int sampler, int n_steps, int modality,
 static int get_graph(MdtHandle* h, int sampler, int n_steps, int modality, int B, GraphEntry** out) {
   GraphKey key{B, n_steps, sampler, modality};
   auto it = h->graphs.find(key);
-  if (it != h->graphs.end()) { *out = &it->second; return 0; }
+  if (it != h->graphs.end()) { it->second.last_use = ++h->use_clock; *out = &it->second; return 0; }
+  // bounded cache (a ~2000-node executable graph per distinct (B, N, sampler, modality)): evict the least recently used
+  while (h->graphs.size() >= MdtHandle::MAX_GRAPHS) {
+    auto lru = h->graphs.begin();
+    for (auto jt = h->graphs.begin(); jt != h->graphs.end(); ++jt) if (jt->second.last_use < lru->second.last_use) lru = jt;
+    drop_graph(lru->second);
+    h->graphs.erase(lru);
+  }
   GraphEntry ge{};
   h->capture_count = 0;
+  if (h->fused) TRY(build_fused_plan(h, B, sampler_evals(h, sampler, n_steps), n_steps, h->mod, 0, h->sigmas, 0, 1, nullptr, &ge.plan));
   static const bool split = !getenv("MDTB200_SINGLE_GRAPH");
-  const int s0 = (split && n_steps > 3) ? 2 : n_steps;
-  TRY(capture_segment(h, sampler, n_steps, modality, B, 0, s0, &ge.exec));
+  const int s0 = (!ge.plan && split && n_steps > 3) ? 2 : n_steps;
+  h->cur_plan = ge.plan;
+  int rc = capture_segment(h, sampler, n_steps, modality, B, 0, s0, &ge.exec);
+  h->cur_plan = nullptr;
+  if (rc) { free_plan(ge.plan); return rc; }
   if (s0 < n_steps) {
-    int rc = capture_segment(h, sampler, n_steps, modality, B, s0, n_steps, &ge.exec2);
-    if (rc) { cudaGraphExecDestroy(ge.exec); return rc; }
+    rc = capture_segment(h, sampler, n_steps, modality, B, s0, n_steps, &ge.exec2);
+    if (rc) { drop_graph(ge); return rc; }
   }
   ge.kernels = h->capture_count;
+  ge.last_use = ++h->use_clock;
   auto ins = h->graphs.emplace(key, ge);
   *out = &ins.first->second;
   return 0;
@@ -916,6 +1193,7 @@ MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* ds
       {"xh", h->xh, M * d}, {"xe", h->xe, M * d}, {"a", h->a, M * d}, {"qkv", h->qkv, M * 3 * d}, {"y", h->y, M * d},
       {"h", h->hbuf, M * 4 * d}, {"q", h->q, M * d}, {"pe", h->pe, (size_t)h->mod_rows * d}, {"cs", h->cs, (size_t)h->mod_rows * d},
       {"x", h->x, M * h->A},
+      {"fused_trace", reinterpret_cast<const float*>(h->fd_trace), h->fd_trace ? (size_t)fd::TRACE_PHASES * 160 * 8 * 2 : 0},
   };
   for (const Ent& e : tab) {
     if (strcmp(e.n, name) == 0) {
