@@ -12,6 +12,10 @@ HOST buffers (H2D of state/goal/x_T and D2H of the actions inside the timed regi
 
 --impl reference: the reference's CPU implementation of the path (the oracle port: same ATen ops, encoder re-run
 on every evaluation exactly like the reference) on the box's host cores, rank 0 only.
+
+Extra records on the default line (rank 0, N=1): `latency` (median / p95 of the timed calls), `variant_6x6` (BASELINE-literal
+6+6 layers), `gpu_torch_baseline` (the same algorithm as stock PyTorch on the same B200: eager fp32, CUDA-graphed fp32, TF32
+with its action error -- the honest GPU competitor), `train` (BASELINE config 3: one training step at batch 512).
 """
 from __future__ import annotations
 
@@ -151,6 +155,56 @@ def cpu_reference_run(enc, dec, B, steps, warmup, budget_s=150.0):
     return value, desc, total / steps * 1e3
 
 
+def train_measure(args, dev, B=512, steps=10, warmup=3):
+    """BASELINE config 3 on one GPU as a sub-record of the default line: diffusion loss forward + backward + optimizer step (the
+    fused multi-tensor AdamW + EMA kernel of this repo) at batch B, shipped dropout probabilities, synthetic batch."""
+    import math
+    from mdt_policy_b200 import GCDenoiser, utils as U
+    from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs
+    enc = dec = args.layers
+    cfgd = inner_cfg(enc, dec, "fp32", B)
+    cfgd.update(dict(attn_pdrop=0.3, resid_pdrop=0.1, mlp_pdrop=0.05))
+    model = GCDenoiser(cfgd, sigma_data=0.5)
+    model.load_state_dict(synthetic_state_dict([(n, p.shape) for n, p in model.named_parameters()], 12, "trained"))
+    model = model.to(dev).train()
+    try:
+        from mdt_policy_b200.optim import FusedAdamWEMA
+        opt = FusedAdamWEMA(model.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.999)
+        opt_name = "mdt_policy_b200.optim.FusedAdamWEMA (one multi-tensor CUDA kernel: AdamW + EMA)"
+    except ImportError:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=0.05)
+        opt_name = "torch.optim.AdamW"
+    inp = synthetic_inputs(B, seed=31)
+    torch.manual_seed(0)
+    sig = U.rand_log_logistic((B,), loc=math.log(0.5), scale=0.5, min_value=0.001, max_value=80.0, device="cpu").to(dev)
+    batch = {k: inp[k].to(dev) for k in ("state_images", "goal", "actions", "noise")}
+    state = {"state_images": batch["state_images"], "modality": "lang"}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss, _ = model.loss(state, batch["actions"], batch["goal"], batch["noise"], sig)
+        loss.backward()
+        opt.step()
+        return loss
+
+    first = float(step())
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        last = step()
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    fwd_flops = B * (F_ENC * enc / 4 + F_KV * dec / 4 + (F_CORE - 107_520) * dec / 4 + 107_520 + 1_179_648 + 1_769_472 * dec)
+    peak = measured_peak_tflops()[0]
+    return {"workload": f"configs[2]: training step, batch={B}, MDT-V {enc}enc+{dec}dec, diffusion loss fwd+bwd+optimizer, dropout 0.3/0.1/0.05",
+            "metric": "training action-tokens/sec", "value": B * 10 / (ms / 1e3), "unit": "action-tokens/s", "ms_per_step": ms, "steps": steps,
+            "optimizer": opt_name, "loss_first": first, "loss_last": float(last),
+            "roofline_frac": 3 * fwd_flops / (ms / 1e3) / 1e12 / peak, "exposed_comm_ms": 0.0}
+
+
 def train_main(args):
     """BASELINE config 3 (1 GPU, batch 512) / config 5 (DDP, global batch = 128 x N... here 512 per GPU unless --batch): one step =
     diffusion loss forward + backward + AdamW update on a synthetic (state tokens, goal, actions) batch.  Metric: action-tokens/s.
@@ -272,11 +326,101 @@ def train_main(args):
     return 0
 
 
+def variant_6x6(args, dev, B):
+    """BASELINE-literal "6 layers" reading of config 2 (6 enc + 6 dec): device-resident throughput over 20 calls."""
+    from mdt_policy_b200 import GCDenoiser, DenoiseAgent
+    from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs
+    model = GCDenoiser(inner_cfg(6, 6, args.precision, B), sigma_data=0.5)
+    model.load_state_dict(synthetic_state_dict([(n, p.shape) for n, p in model.named_parameters()], 13, "trained"))
+    model = model.to(dev).eval()
+    agent = DenoiseAgent(model, device=dev, num_sampling_steps=N_STEPS, sampler_type="ddim", noise_scheduler="exponential",
+                         sigma_min=SIGMA_MIN, sigma_max=SIGMA_MAX)
+    inp = synthetic_inputs(B, seed=23)
+    state = {"state_images": inp["state_images"].to(dev), "modality": "lang"}
+    goal, xT = inp["goal"].to(dev), inp["x_T"].to(dev)
+    for _ in range(3):
+        agent.denoise_actions(None, state, goal, inference=True, x_T=xT)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 20
+    s.record()
+    for _ in range(k):
+        agent.denoise_actions(None, state, goal, inference=True, x_T=xT)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / k
+    fl = alg_flops(B, N_STEPS, 6, 6)
+    return {"workload": "6 enc + 6 dec, same batch / sampler", "value": N_STEPS / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+            "roofline_frac": fl / (ms / 1e3) / 1e12 / measured_peak_tflops()[0], "l2": "not flushed (20 back-to-back calls)"}
+
+
+def gpu_torch_baseline(enc, dec, B, dev):
+    """The same algorithm as stock PyTorch on the same GPU (the reference ships no Blackwell kernel, so this is its honest GPU
+    competitor): the oracle port's ATen ops on cuda, encoder recomputed per evaluation exactly like the reference.
+    eager fp32 ("highest"), the same under a CUDA graph, and TF32 matmuls with the action error they introduce."""
+    from oracle import mdt_oracle as orc
+    from mdt_policy_b200 import GCDenoiser
+    from mdt_policy_b200.synthetic import synthetic_state_dict, synthetic_inputs
+    shapes = [(n, p.shape) for n, p in GCDenoiser(inner_cfg(enc, dec, "fp32", B), sigma_data=0.5).named_parameters()]
+    P = {k: v.to(dev) for k, v in synthetic_state_dict(shapes, 12, "trained").items()}
+    cfg = orc.OracleCfg(n_enc_layers=enc, n_dec_layers=dec)
+    inp = synthetic_inputs(B, seed=22)
+    st = {"state_images": inp["state_images"].to(dev), "modality": "lang"}
+    goal, xT = inp["goal"].to(dev), inp["x_T"].to(dev)
+    sig = orc.get_sigmas_exponential(N_STEPS, SIGMA_MIN, SIGMA_MAX).to(dev)
+
+    def call():
+        return orc.sample(P, cfg, st, xT, goal, sig, "ddim")
+
+    def time_calls(fn, k=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / k
+
+    out = {"unit": UNIT, "what": f"oracle port (ATen ops of the reference) on cuda, torch {torch.__version__}, B={B}, encoder per evaluation"}
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.get_float32_matmul_precision())
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.set_float32_matmul_precision("highest")
+        ref = call()
+        ms = time_calls(call)
+        out["eager_fp32"] = {"value": N_STEPS / (ms / 1e3), "ms_per_call": ms}
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                call()
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(g):
+                gout = call()
+            ms = time_calls(g.replay)
+            out["graphed_fp32"] = {"value": N_STEPS / (ms / 1e3), "ms_per_call": ms, "err_vs_eager": float((gout - ref).abs().max())}
+        except Exception as e:  # noqa: BLE001
+            out["graphed_fp32"] = {"error": repr(e)[:200]}
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.set_float32_matmul_precision("high")
+        tf = call()
+        ms = time_calls(call)
+        out["tf32"] = {"value": N_STEPS / (ms / 1e3), "ms_per_call": ms, "err": float((tf - ref).abs().max()),
+                       "note": "max |actions - fp32 actions|; the parity gate is 1e-4"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev[0], prev[1]
+        torch.set_float32_matmul_precision(prev[2])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MDTB200_PRECISION", "bf16x3"))
     ap.add_argument("--batch", type=int, default=256, help="environments per GPU")
@@ -337,6 +481,8 @@ def main():
     def host_call():
         return agent.denoise_actions_host(host["state_images"], host["goal"], host["x_T"], "lang", out_host)
 
+    call_ms = {}
+
     def timed(fn, k):
         evs = []
         for _ in range(k):
@@ -345,7 +491,11 @@ def main():
             s.record(); fn(); e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in evs) / 1e3
+        call_ms[fn.__name__] = sorted(s.elapsed_time(e) for s, e in evs)
+        return sum(call_ms[fn.__name__]) / 1e3
+
+    def pct(v, q):
+        return v[min(len(v) - 1, int(q * len(v)))]
 
     for _ in range(warmup):
         device_call(); host_call()
@@ -379,43 +529,68 @@ def main():
         "metric": METRIC, "value": agg["throughput"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16x3": "bf16x3 (split-fp32 on tcgen05, fp32 accumulate)", "fp32": "f32", "bf16": "bf16"}[args.precision],
-        "data": "synthetic", "config": dict(config, l2="flushed between timed iterations (256 MiB write)", precision=args.precision),
+        "data": "synthetic", "config": config, "precision": args.precision, "l2": "flushed between timed iterations (256 MiB write)",
         "e2e": {"value": agg_e2e["throughput"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4,
                 "ms_per_step": agg_e2e["seconds"] / args.steps * 1e3},
         "gpu_launches": int(launches),
+        "latency": {"unit": "ms per 10-step sampling call", "calls": args.steps,
+                    "device": {"median": pct(call_ms["device_call"], 0.5), "p95": pct(call_ms["device_call"], 0.95), "min": call_ms["device_call"][0]},
+                    "e2e": {"median": pct(call_ms["host_call"], 0.5), "p95": pct(call_ms["host_call"], 0.95), "min": call_ms["host_call"][0]}},
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "whole sampling graph (encode + 10 steps), algorithmic FLOPs ALG(B,N) of SURVEY 8d",
                      "alg_gflop_per_launch": flops / 1e9, "peak_source": peak_src},
     }
-    # Dominant kernel = tc::tc_gemm_kernel (72 % of kernel time, profiles/r01_v7_summary.md).  Kernels inside a CUDA graph cannot be
-    # bracketed by events one by one, so each decoder GEMM shape is timed live here with CUDA events over 200 back-to-back launches
-    # (mdtb200_debug_gemm_time, L2-warm, same kernel/instantiation the graph uses at M = B*10) and weighted by its launch count per
-    # decoder layer.  The whole-graph figure (all kernels, ALG(B,N) of SURVEY 8d over the timed calls) is kept as `whole_graph`.
-    whole = line["roofline"]
+    # The top-level roofline is the WHOLE timed graph (all kernels, ALG(B,N) of SURVEY 8d over the timed calls).  `dominant_kernel`
+    # describes tc::tc_gemm_kernel (~68 % of kernel time, profiles/r02_launches_summary.md) as the graph runs it: kernels inside a CUDA
+    # graph cannot be bracketed by events one by one, so each decoder GEMM is timed live with CUDA events over 200 back-to-back launches
+    # of the same instantiation (mdtb200_debug_gemm_time: per-branch M = B*10/branches rows, the tile width launch_tc_gemm picks there,
+    # pseudo-random non-zero operands) and weighted by its launches per decoder layer.  `traffic` comes from the committed ncu capture.
     if args.precision != "fp32":
         try:
             eng = list(model.inner_model._engines.values())[0]
-            M, d = B * 10, 384
-            shapes = {"qkv (N=3d,K=d)": (M, 3 * d, d, 0, 1), "attn/cross c_proj, cross q (N=d,K=d,+res)": (M, d, d, 4, 3),
+            branches = int(os.environ.get("MDTB200_BRANCHES", "4"))
+            while branches > 1 and B // branches < 32:
+                branches -= 1
+            M, d = (B // branches) * 10, 384
+            shapes = {"qkv (N=3d,K=d)": (M, 3 * d, d, 0, 1), "attn c_proj + gate + res (N=d,K=d)": (M, d, d, 5, 1),
                       "mlp c_fc + GELU (N=4d,K=d)": (M, 4 * d, d, 1, 1), "mlp c_proj + gate + res (N=d,K=4d)": (M, d, 4 * d, 5, 1)}
-            per, tot_flop, tot_us = {}, 0.0, 0.0
+            per, tot_flop, tot_us, n_l = {}, 0.0, 0.0, 0
             for name, (m, n, k, epi, count) in shapes.items():
                 us = eng.gemm_time_us(m, n, k, epi, 200)
                 per[name] = {"us_per_launch": us, "launches_per_layer": count, "alg_tflops": 2.0 * m * n * k / us / 1e6,
                              "frac": 2.0 * m * n * k / us / 1e6 / peak}
                 tot_flop += 2.0 * m * n * k * count
                 tot_us += us * count
+                n_l += count
             ach = tot_flop / tot_us / 1e6
-            line["roofline"] = {
-                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 1300,
-                "kernel": "tc::tc_gemm_kernel<BN,3> (tcgen05 bf16x3 GEMM), launch-weighted over the 6 GEMMs of a decoder layer at M=%d" % M,
-                "alg_gflop_per_launch": tot_flop / 6 / 1e9, "us_per_launch": tot_us / 6, "peak_source": peak_src,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_v7_summary.md): L2-resident",
-                "note": "bf16x3 issues 3x the algorithmic FLOPs, ceiling 1/3; per-SM operand ingest (~64 B/clk) is the binding limit, see DESIGN.md",
-                "shapes": per, "whole_graph": whole}
+            traffic, traffic_src = None, None
+            try:
+                with open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            except Exception:  # noqa: BLE001
+                pass
+            line["roofline"]["traffic"] = traffic
+            line["roofline"]["traffic_source"] = traffic_src
+            line["dominant_kernel"] = {
+                "kernel": "tc::tc_gemm_kernel<BN,3> (tcgen05 bf16x3 GEMM), launch-weighted over the %d GEMMs of a decoder layer at the "
+                          "per-branch M=%d the graph runs (%d concurrent sub-batch chains)" % (n_l, M, branches),
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "alg_gflop_per_launch": tot_flop / n_l / 1e9, "us_per_launch": tot_us / n_l, "traffic": traffic,
+                "note": "timed alone (one chain, back-to-back launches); bf16x3 issues 3x the algorithmic FLOPs (ceiling 1/3)",
+                "shapes": per}
         except Exception as e:  # noqa: BLE001
-            line["roofline"]["dominant_kernel_error"] = repr(e)
+            line["dominant_kernel"] = {"error": repr(e)}
+    if world == 1:
+        for name, fn in (("variant_6x6", lambda: variant_6x6(args, dev, B)), ("gpu_torch_baseline", lambda: gpu_torch_baseline(enc, dec, B, dev)),
+                         ("train", lambda: train_measure(args, dev, 512, 10, 3))):
+            if os.environ.get("MDTB200_BENCH_SKIP_EXTRAS"):
+                break
+            try:
+                line[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                line[name] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         _, desc, _ = cpu_reference_run(enc, dec, B, steps=5, warmup=2, budget_s=40.0)
         line["cpu_baseline"] = desc

@@ -174,6 +174,10 @@ MDTB200_API int mdtb200_op_gate_res(const float* x, const float* f, const float*
 MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const float* gate, float* df, float* prod, int M, int d,
                                         int rows_per_group, void* stream);
 
+/* Kernel timeline of everything the library launches (debugging / profiling aid, tools/ktrace.py): capacity > 0 arms the
+ * trace, capacity == 0 copies up to max_records {globaltimer ns, tag|event|sm|grid|block} pairs to dst_host and disarms. */
+MDTB200_API int64_t mdtb200_debug_ktrace(MdtHandle* h, int64_t capacity, unsigned long long* dst_host, int64_t max_records);
+
 /* tests only: out (M,N) = epi(A (M,K) . W (N,K)^T + bias) through the tensor-core GEMM kernel on fp32 inputs
  * (epi: 0 none, 1 GELU, 4 residual R (M,N), 5 residual + gate[(m / rows_per_group), n] (gate row stride N)). */
 MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W, const float* bias, const float* R,

@@ -20,7 +20,7 @@ EXPORTS = [
     "mdtb200_abi_version", "mdtb200_create", "mdtb200_destroy", "mdtb200_last_error",
     "mdtb200_bind_weight", "mdtb200_commit_weights", "mdtb200_encode", "mdtb200_set_context",
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
-    "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time",
+    "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time", "mdtb200_debug_ktrace",
     "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
     "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout",
 ]
@@ -71,6 +71,8 @@ def _declare(lib):
     lib.mdtb200_debug_gemm.restype = i32
     lib.mdtb200_debug_gemm_time.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_float), vp]
     lib.mdtb200_debug_gemm_time.restype = i32
+    lib.mdtb200_debug_ktrace.argtypes = [vp, i64, vp, i64]
+    lib.mdtb200_debug_ktrace.restype = i64
     lib.mdtb200_op_gemm.argtypes = [i32, fp, fp, fp, fp, i32, i32, i32, i32, vp]
     lib.mdtb200_op_gemm_tc.argtypes = [i32, fp, fp, fp, fp, i32, i32, i32, vp, vp]
     lib.mdtb200_op_gemm_tc.restype = i32
@@ -102,7 +104,7 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
-        if not os.path.exists(path):
+        if _build.is_stale():             # missing, or built from other sources (content hash); build() is multi-process safe
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001

@@ -90,8 +90,9 @@ class DenoiseAgent:
         dev = self.device
         inner = getattr(self.model, "inner_model", None)
         fused = self.sampler_type in ("ddim", "euler", "heun", "dpmpp_2m") and getattr(inner, "_variant", None) == "mdtv"
-        if (fused and not state_images_host.is_cuda and state_images_host.dtype == torch.float32 and state_images_host.is_contiguous()
-                and latent_goal_host.is_contiguous() and x_T_host.is_contiguous()):
+        host_ok = all((not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous()
+                      for t in (state_images_host, latent_goal_host, x_T_host))     # raw float* through the C ABI: no silent casts
+        if fused and host_ok:
             # straight through the C ABI's host-buffer entry point: no intermediate CUDA tensors on the Python side
             if self.model.training:
                 self.model.eval()
@@ -139,6 +140,7 @@ class DenoiseAgent:
 
     # mdtv_agent.py:508-521 (forward value; see GCDenoiser.loss about the backward pass)
     def diffusion_loss(self, perceptual_emb, latent_goal, actions):
+        self.model.train()               # as the reference (:517): sampling / validation may have left the model in eval mode
         sigmas = self.make_sample_density()(shape=(len(actions),), device=self.device).to(self.device)
         noise = torch.randn_like(actions)
         loss, _ = self.model.loss(perceptual_emb, actions, latent_goal, noise, sigmas)

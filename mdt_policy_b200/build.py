@@ -6,6 +6,8 @@ serves as the CPU-side "does it build" check (``__graft_entry__.build``).
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -34,26 +36,61 @@ def find_nvcc() -> str:
     return nvcc
 
 
+HASH_PATH = LIB_PATH + ".srchash"      # sha256 of the sources the library was built from (travels with the .so)
+LOCK_PATH = LIB_PATH + ".lock"
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    for p in SOURCES + HEADERS:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
+    """True when the library is missing or was built from different sources (content hash, not mtimes: a snapshot copied to
+    another machine keeps its hash).  A library without a hash file is trusted as long as it exists."""
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS if os.path.exists(p))
+    if not os.path.exists(HASH_PATH):
+        return False
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds in-tree.  Safe under torchrun: one process compiles (file lock, private temp file, atomic rename), the others wait
+    and find the finished library."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr, file=sys.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    with open(LOCK_PATH, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():      # another process finished the build while we waited for the lock
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = [find_nvcc(), *NVCC_FLAGS, "-o", tmp, *SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr, file=sys.stderr)
+            os.replace(tmp, LIB_PATH)
+            with open(HASH_PATH + ".tmp", "w") as f:
+                f.write(source_hash())
+            os.replace(HASH_PATH + ".tmp", HASH_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

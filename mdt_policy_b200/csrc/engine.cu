@@ -37,6 +37,7 @@ struct EncLayerW {
 struct DecLayerW {
   const float *ln1_w, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln3_w, *ln3_b, *wq, *bq, *wco, *bco, *ln2_w, *ln2_b, *wfc, *bfc, *wproj, *bproj;
   const __nv_bfloat16 *wqkv16, *wo16, *wq16, *wco16, *wfc16, *wproj16;
+  const __nv_bfloat16 *wgx16, *wux16;     // stacked per-head operands of the algebraic cross-attention tables (H*d, 2*64)
 };
 struct Weights {
   const float *goal0_w, *goal0_b, *goal2_w, *goal2_b;
@@ -46,7 +47,7 @@ struct Weights {
   std::vector<EncLayerW> enc;
   std::vector<DecLayerW> dec;
   const float *enc_ln_w, *enc_ln_b, *dec_ln_w, *dec_ln_b;
-  const float *wkv_all, *bkv_all, *wmod_all, *bmod_all;
+  const float *wkv_all, *bkv_all, *wmod_all, *bmod_all, *bq_all;
   const __nv_bfloat16 *wkv_all16;
   const float *sig1_w, *sig1_b, *sig3_w, *sig3_b;
   const float *ae_w, *ae_b, *ap_w, *ap_b;
@@ -77,6 +78,8 @@ struct GraphEntry { cudaGraphExec_t exec; cudaGraphExec_t exec2; int64_t kernels
 struct Work {
   float *in_goal, *in_state, *x, *x2, *dbuf, *gh, *xe, *ctx, *kv, *xh, *a, *qkv, *y, *hbuf, *q;
   __nv_bfloat16 *a16, *y16, *h16;
+  // algebraic cross-attention (cross_row_kernel): head-major key / value operands and the G / U / c tables of layer 0
+  __nv_bfloat16 *ka16, *va16; float *gtab, *utab, *ctab;
 };
 
 struct MdtHandle {
@@ -99,6 +102,10 @@ struct MdtHandle {
   float *pe = nullptr, *sh = nullptr, *cs = nullptr, *mod = nullptr;
   __nv_bfloat16 *a16 = nullptr, *y16 = nullptr, *h16 = nullptr;   // split-bf16 operand copies (hi | lo)
   int mod_rows = 0;
+  // algebraic cross-attention tables (see cross_row_kernel); per-layer strides in elements
+  bool cross_fused = false;
+  __nv_bfloat16 *ka16 = nullptr, *va16 = nullptr; float *gtab = nullptr, *utab = nullptr, *ctab = nullptr;
+  size_t cross_rows = 0, ka_layer_stride = 0, tab_layer_stride = 0, ctab_layer_stride = 0;
 
   // persistent fused decoder (fused_decoder.cuh): split-K partial sums (C, Mp, d) and per-row-group progress counters
   bool fused = false; int fd_C = 0, fd_SPG = 0, fd_groups_max = 0;
@@ -115,9 +122,10 @@ struct MdtHandle {
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES] = {};
   int branches = 4;               // MDTB200_BRANCHES overrides
 
-  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16}; }
-  // view of samples [b0, ...): every buffer is row-indexed by sample (encoder rows reuse the decoder row offsets, Tc <= T)
-  Work slice(const Work& w, int b0) const {
+  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16, ka16, va16, gtab, utab, ctab}; }
+  // view of samples [b0, ...): every buffer is row-indexed by sample (encoder rows reuse the decoder row offsets, Tc <= T);
+  // mc_off = padded context rows of the sub-batches before this one (each sub-batch owns a 128-row aligned block per head)
+  Work slice(const Work& w, int b0, int mc_off = 0) const {
     const size_t r = (size_t)b0 * T, dd = d;
     Work o = w;
     o.in_goal += (size_t)b0 * cfg.goal_dim; o.in_state += (size_t)b0 * Ts * cfg.obs_dim;
@@ -125,6 +133,10 @@ struct MdtHandle {
     o.xe += r * dd; o.ctx += (size_t)b0 * Tc * dd; o.kv += (size_t)b0 * Tc * Ld * 2 * dd;
     o.xh += r * dd; o.a += r * dd; o.qkv += r * 3 * dd; o.y += r * dd; o.hbuf += r * 4 * dd; o.q += r * dd;
     if (o.a16) { o.a16 += r * 2 * dd; o.y16 += r * 2 * dd; o.h16 += r * 8 * dd; }
+    if (o.gtab) {
+      const size_t hr = (size_t)H * mc_off;
+      o.ka16 += hr * 128; o.va16 += hr * 128; o.gtab += hr * dd; o.utab += hr * dd; o.ctab += (size_t)b0 * H * Tc;
+    }
     return o;
   }
   std::map<GraphKey, GraphEntry> graphs;
@@ -177,6 +189,7 @@ struct Gemm {
   const float* gate = nullptr; int gate_stride = 0; int rows_per_group = 1;
   int M = 0, N = 0, K = 0; int epi = EPI_NONE;
   int gi = 0, go = 0, goff = 0;
+  int wg_rows = 0, wg_stride = 0, w_rows = 0;          // weight groups (tensor-core path only)
 };
 
 int launch_sgemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
@@ -218,6 +231,7 @@ int gemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
     t.M = p.M; t.N = p.N; t.K = p.K; t.epi = p.epi;
     t.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1;
     t.trace = nullptr; t.gi = p.gi; t.go = p.go; t.goff = p.goff;
+    t.wg_rows = p.wg_rows; t.wg_stride = p.wg_stride; t.w_rows = p.w_rows;
     const char* e = tc::launch_tc_gemm(h->tma, t, st);
     if (e) return fail(h, MDTB200_ECUDA, "tcgen05 gemm (M=%d N=%d K=%d): %s", p.M, p.N, p.K, e);
     count_launch(h);
@@ -296,13 +310,41 @@ int branch_count(const MdtHandle* h, int B) {
   return nb;
 }
 
+inline int round128(int v) { return (v + 127) / 128 * 128; }
+
+// G / U / c tables of the algebraic cross-attention for the B samples of this (sub-)batch (kernels_simt.cuh, cross_row_kernel):
+// one packing kernel for all layers, then two head-grouped tensor-core GEMMs per layer (K = head_dim padded to 64).
+int compute_cross_tables(MdtHandle* h, const Work& k, int B, cudaStream_t st) {
+  const int d = h->d, H = h->H, Tc = h->Tc, Mc = B * Tc, mcp = round128(Mc), Ld = h->Ld;
+  CrossPackArgs a{};
+  a.kv = k.kv; a.ldkv = Ld * 2 * d; a.bq_all = h->w.bq_all; a.ka = k.ka16; a.va = k.va16; a.layer_stride16 = h->ka_layer_stride;
+  a.ctab = k.ctab; a.ctab_layer_stride = h->ctab_layer_stride; a.Mc = Mc; a.mcp = mcp; a.Tc = Tc; a.H = H; a.hd = h->hd; a.d = d; a.L = Ld;
+  const int n = H * mcp * 64;
+  launch_pdl(pack_cross_operands_kernel, dim3((n + 255) / 256, Ld), dim3(256), 0, st, a);
+  count_launch(h);
+  TRY(check_launch(h, "pack_cross_operands_kernel"));
+  for (int l = 0; l < Ld; ++l) {
+    for (int which = 0; which < 2; ++which) {
+      Gemm g;
+      g.A16 = (which ? k.va16 : k.ka16) + (size_t)l * h->ka_layer_stride; g.lda16 = 128;
+      g.W16 = which ? h->w.dec[l].wux16 : h->w.dec[l].wgx16; g.w_rows = H * d; g.wg_rows = mcp; g.wg_stride = d;
+      g.C = (which ? k.utab : k.gtab) + (size_t)l * h->tab_layer_stride; g.ldc = d;
+      g.M = H * mcp; g.N = d; g.K = 64;
+      TRY(gemm(h, g, st));
+    }
+  }
+  return 0;
+}
+
 // cross-attention K/V of every decoder layer from the context: kv[Mc, L*2d] = ctx . Wkv_all^T + b
 int compute_kv(MdtHandle* h, const Work& k, int B, cudaStream_t st, bool ctx_split_valid = false) {
   Gemm g;
   g.A = k.ctx; g.lda = h->d; g.W = h->w.wkv_all; g.bias = h->w.bkv_all; g.C = k.kv; g.ldc = h->Ld * 2 * h->d;
   g.M = B * h->Tc; g.N = h->Ld * 2 * h->d; g.K = h->d;
   if (ctx_split_valid) { g.A16 = k.a16; g.lda16 = 2 * h->d; g.W16 = h->w.wkv_all16; }
-  return gemm(h, g, st);
+  TRY(gemm(h, g, st));
+  if (h->cross_fused) TRY(compute_cross_tables(h, k, B, st));
+  return 0;
 }
 
 // forward_enc_only (mdtv_transformer.py:213-222; mdt_transformer.py:211-229 for the MDT variant)
@@ -439,6 +481,20 @@ int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mo
     o.gate = ml + 2 * d; o.gate_stride = mod_stride; o.rows_per_group = T; o.M = M; o.N = d; o.K = d; o.epi = EPI_RES_GATE;
     TRY(gemm(h, o, st));
     // x += CrossAttn_causal-top-left(LN3(x), ctx)       (ln3 is nn.LayerNorm with bias)
+    if (h->cross_fused) {
+      // algebraic form on the per-call G / U tables: LN3 -> scores -> softmax -> output projection -> residual -> LN2 + modulate
+      CrossRowArgs ca{};
+      ca.xh = k.xh; ca.gtab = k.gtab + (size_t)l * h->tab_layer_stride; ca.utab = k.utab + (size_t)l * h->tab_layer_stride;
+      ca.ctab = k.ctab + (size_t)l * h->ctab_layer_stride; ca.mcp = round128(B * Tc);
+      ca.ln3_w = L.ln3_w; ca.ln3_b = L.ln3_b; ca.bco = L.bco; ca.ln2_w = L.ln2_w; ca.ln2_b = L.ln2_b;
+      ca.shift = ml + 3 * d; ca.scale = ml + 4 * d; ca.mod_stride = mod_stride;
+      ca.a16 = k.a16; ca.ld16 = 2 * d; ca.lo_off = d; ca.B = B; ca.T = T; ca.Tc = Tc; ca.H = h->H; ca.d = d;
+      const size_t smem = cross_row_smem_bytes(d, T, Tc, h->H);
+      if (d == 384) launch_pdl(cross_row_kernel<3>, dim3(B), dim3(CR_THREADS), smem, st, ca);
+      else launch_pdl(cross_row_kernel<4>, dim3(B), dim3(CR_THREADS), smem, st, ca);
+      count_launch(h);
+      TRY(check_launch(h, "cross_row_kernel"));
+    } else {
     TRY(launch_ln(h, k.xh, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln3_w, L.ln3_b, nullptr, nullptr, 0, M, st));
     Gemm cq;
     cq.A = k.a; cq.lda = d; cq.A16 = k.a16; cq.lda16 = 2 * d; cq.W = L.wq; cq.W16 = L.wq16; cq.bias = L.bq; cq.C = k.q; cq.ldc = d; cq.M = M; cq.N = d; cq.K = d;
@@ -450,6 +506,7 @@ int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mo
     TRY(gemm(h, co, st));
     // x += gate_mlp * MLP(shift_mlp + LN2(x) * scale_mlp)
     TRY(launch_ln(h, k.xh, tcp ? nullptr : k.a, tcp ? k.a16 : nullptr, L.ln2_w, L.ln2_b, ml + 3 * d, ml + 4 * d, mod_stride, M, st));
+    }
     Gemm f;
     f.A = k.a; f.lda = d; f.A16 = k.a16; f.lda16 = 2 * d; f.W = L.wfc; f.W16 = L.wfc16; f.bias = L.bfc;
     f.C = tcp ? nullptr : k.hbuf; f.ldc = 4 * d; f.C16 = tcp ? k.h16 : nullptr; f.ldc16 = 8 * d; f.lo_off = 4 * d;
@@ -729,11 +786,13 @@ int sample_body(MdtHandle* h, int sampler, int n_steps, int modality, int B, cud
     rc = sample_steps(h, base, sampler, n_steps, modality, B, st, step_begin, enc_end);
   } else {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    int mc_off = 0;
     for (int s = 0; s < nb && !rc; ++s) {
       const int b0 = (int)((long long)B * s / nb), b1 = (int)((long long)B * (s + 1) / nb);
       cudaStream_t bs = h->branch_streams[s];
       CUDA_TRY(h, cudaStreamWaitEvent(bs, h->ev_fork, 0));
-      rc = sample_steps(h, h->slice(base, b0), sampler, n_steps, modality, b1 - b0, bs, step_begin, enc_end);
+      rc = sample_steps(h, h->slice(base, b0, mc_off), sampler, n_steps, modality, b1 - b0, bs, step_begin, enc_end);
+      mc_off += round128((b1 - b0) * h->Tc);
       CUDA_TRY(h, cudaEventRecord(h->ev_join[s], bs));
       CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[s], 0));
     }
@@ -810,7 +869,7 @@ size_t arena_size(const MdtHandle* h) {
   n += 2 * (d * O + d) + 64 * d;                           // tok_emb, incam_embed, pos_emb
   n += h->Le * (12 * d * d + 3 * d + 8 * d + 64 * 12);      // encoder layers (+optional biases/padding)
   n += h->Ld * (14 * d * d + 3 * d + d + 12 * d + 64 * 18); // decoder layers
-  n += h->Ld * (2 * d * d + 2 * d) + h->Ld * (6 * d * d + 6 * d);
+  n += h->Ld * (2 * d * d + 2 * d) + h->Ld * (6 * d * d + 6 * d) + h->Ld * (d + 64);
   n += 4 * d + 2 * d * d * 2 + 3 * d + A * d * 2 + d + A + 64 * 64;
   return n + (1 << 16);
 }
@@ -858,7 +917,7 @@ int pack_weights(MdtHandle* h, cudaStream_t st) {
   }
   w.enc_ln_w = pk.copy("encoder.ln.weight", d); w.enc_ln_b = pk.copy("encoder.ln.bias", d, true);
   w.dec.resize(h->Ld);
-  std::vector<std::pair<std::string, int64_t>> kvw, kvb, modw, modb;
+  std::vector<std::pair<std::string, int64_t>> kvw, kvb, modw, modb, bqv;
   for (int l = 0; l < h->Ld && pk.ok; ++l) {
     DecLayerW& L = w.dec[l];
     std::string b = "decoder.blocks." + std::to_string(l) + ".";
@@ -874,13 +933,25 @@ int pack_weights(MdtHandle* h, cudaStream_t st) {
     L.wproj = pk.copy(b + "mlp.c_proj.weight", 4 * d * d); L.bproj = pk.copy(b + "mlp.c_proj.bias", d, true);
     L.wqkv16 = pk.split(L.wqkv, 3 * d, (int)d); L.wo16 = pk.split(L.wo, d, (int)d); L.wq16 = pk.split(L.wq, d, (int)d);
     L.wco16 = pk.split(L.wco, d, (int)d); L.wfc16 = pk.split(L.wfc, 4 * d, (int)d); L.wproj16 = pk.split(L.wproj, d, (int)(4 * d));
+    if (h->cross_fused && L.wq && L.wco && pk.ok) {
+      const size_t n = (size_t)h->H * d * 128;
+      if (h->arena16_used + 2 * n > h->arena16_elems) { pk.ok = false; fail(h, MDTB200_ENOMEM, "bf16 weight arena overflow"); }
+      else {
+        __nv_bfloat16* wg = h->arena16 + h->arena16_used; __nv_bfloat16* wu = wg + n;
+        h->arena16_used += 2 * n;
+        const int tot = h->H * (int)d * 64;
+        pack_cross_weights_kernel<<<(tot + 255) / 256, 256, 0, st>>>(L.wq, L.wco, wg, wu, (int)d, h->H, h->hd);
+        L.wgx16 = wg; L.wux16 = wu;
+      }
+    }
+    bqv.push_back({b + "cross_att.query.bias", d});
     kvw.push_back({b + "cross_att.key.weight", d * d}); kvw.push_back({b + "cross_att.value.weight", d * d});
     kvb.push_back({b + "cross_att.key.bias", d}); kvb.push_back({b + "cross_att.value.bias", d});
     modw.push_back({b + "adaLN_zero.modulation.1.weight", 6 * d * d}); modb.push_back({b + "adaLN_zero.modulation.1.bias", 6 * d});
   }
   if (pk.ok) {
     w.wkv_all = pk.concat(kvw); w.bkv_all = pk.concat(kvb);
-    w.wmod_all = pk.concat(modw); w.bmod_all = pk.concat(modb);
+    w.wmod_all = pk.concat(modw); w.bmod_all = pk.concat(modb); w.bq_all = pk.concat(bqv);
     w.wkv_all16 = pk.split(w.wkv_all, (int64_t)h->Ld * 2 * d, (int)d);
   }
   w.dec_ln_w = pk.copy("decoder.ln.weight", d); w.dec_ln_b = pk.copy("decoder.ln.bias", d, true);
@@ -963,7 +1034,8 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   h->arena_floats = arena_size(h);
   if ((rc = dev_alloc(h, &h->arena, h->arena_floats))) return bail(rc);
   if (cfg->precision != MDTB200_PREC_FP32) {
-    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 16 * Dd * Dd + 2 * (2 * Dd * cfg->goal_dim + 2 * Dd * Dd) + 2 * Dd * cfg->obs_dim) + (1 << 16);
+    h->arena16_elems = 2 * ((size_t)h->Le * 12 * Dd * Dd + (size_t)h->Ld * 16 * Dd * Dd + 2 * (2 * Dd * cfg->goal_dim + 2 * Dd * Dd) + 2 * Dd * cfg->obs_dim) + (1 << 16) +
+                       (size_t)h->Ld * 2 * h->H * Dd * 128;
     if ((rc = dev_alloc(h, &h->arena16, h->arena16_elems))) return bail(rc);
   }
   h->mod_rows = (int)(B > (size_t)MAX_STEPS ? B : (size_t)MAX_STEPS);
@@ -981,6 +1053,26 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
     const size_t Mp = (M + 127) / 128 * 128;
     if ((rc = dev_alloc(h, &h->a16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->y16, Mp * 2 * Dd)) || (rc = dev_alloc(h, &h->h16, Mp * 8 * Dd))) return bail(rc);
     cudaMemset(h->a16, 0, Mp * 2 * Dd * 2); cudaMemset(h->y16, 0, Mp * 2 * Dd * 2); cudaMemset(h->h16, 0, Mp * 8 * Dd * 2);
+  }
+  {
+    // algebraic cross-attention (cross_row_kernel): needs the shapes its register / thread budget was written for
+    const char* off = getenv("MDTB200_CROSS_FUSED");
+    const int HT = h->H * h->Tc;
+    const size_t smem = cross_row_smem_bytes(d, h->T, h->Tc, h->H);
+    if (cfg->precision != MDTB200_PREC_FP32 && !(off && off[0] == '0') && (d == 384 || d == 512) && h->hd <= 64 && HT * (d / 4) <= 8 * CR_THREADS &&
+        h->T * 32 < CR_THREADS && h->T * HT <= CR_THREADS * 4 && h->T * h->H <= CR_THREADS && smem <= 200 * 1024) {
+      if (cudaFuncSetAttribute(cross_row_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+          cudaFuncSetAttribute(cross_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        fail(h, MDTB200_ECUDA, "cross_row_kernel needs %zu bytes of shared memory", smem); return bail(MDTB200_ECUDA);
+      }
+      h->cross_rows = (size_t)h->H * (round128((int)B * h->Tc) + 128 * MdtHandle::MAX_BRANCHES);
+      h->ka_layer_stride = h->cross_rows * 128; h->tab_layer_stride = h->cross_rows * Dd; h->ctab_layer_stride = B * HT;
+      if ((rc = dev_alloc(h, &h->ka16, h->Ld * h->ka_layer_stride)) || (rc = dev_alloc(h, &h->va16, h->Ld * h->ka_layer_stride)) ||
+          (rc = dev_alloc(h, &h->gtab, h->Ld * h->tab_layer_stride)) || (rc = dev_alloc(h, &h->utab, h->Ld * h->tab_layer_stride)) ||
+          (rc = dev_alloc(h, &h->ctab, h->Ld * h->ctab_layer_stride))) return bail(rc);
+      cudaMemset(h->ka16, 0, h->Ld * h->ka_layer_stride * 2); cudaMemset(h->va16, 0, h->Ld * h->ka_layer_stride * 2);
+      h->cross_fused = true;
+    }
   }
   if (cfg->precision != MDTB200_PREC_FP32 && (d == 384 || d == 512) && 128 / h->T >= 1 && h->A <= 32) {
     // persistent fused decoder: C = d / 64 CTAs per row group of SPG = 128 / T samples (fused_decoder.cuh)
@@ -1205,6 +1297,32 @@ MDTB200_API int64_t mdtb200_debug_copy(MdtHandle* h, const char* name, float* ds
   return fail(h, MDTB200_EINVAL, "debug_copy: unknown buffer '%s'", name);
 }
 
+// Kernel timeline (tools/ktrace.py): capacity > 0 arms the trace (allocates capacity records), capacity == 0 copies up to
+// `max_records` {time, info} pairs to dst_host, disarms and frees.  Returns the number of records written (or a negative code).
+MDTB200_API int64_t mdtb200_debug_ktrace(MdtHandle* h, int64_t capacity, unsigned long long* dst_host, int64_t max_records) {
+  if (!h) return MDTB200_EINVAL;
+  static unsigned long long* buf = nullptr;
+  static unsigned int cap = 0;
+  cudaDeviceSynchronize();
+  if (capacity > 0) {
+    if (buf) cudaFree(buf);
+    if (cudaMalloc(&buf, (size_t)capacity * 16) != cudaSuccess) return fail(h, MDTB200_ENOMEM, "ktrace: allocation failed");
+    cap = (unsigned int)capacity;
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_ktrace_n, &zero, sizeof(zero)); cudaMemcpyToSymbol(g_ktrace_cap, &cap, sizeof(cap)); cudaMemcpyToSymbol(g_ktrace, &buf, sizeof(buf));
+    return 0;
+  }
+  unsigned int n = 0;
+  unsigned long long* nullp = nullptr;
+  cudaMemcpyFromSymbol(&n, g_ktrace_n, sizeof(n));
+  cudaMemcpyToSymbol(g_ktrace, &nullp, sizeof(nullp));
+  if (n > cap) n = cap;
+  if ((int64_t)n > max_records) n = (unsigned int)max_records;
+  if (buf && dst_host && n) cudaMemcpy(dst_host, buf, (size_t)n * 16, cudaMemcpyDeviceToHost);
+  if (buf) { cudaFree(buf); buf = nullptr; }
+  return (int64_t)n;
+}
+
 // Standalone tensor-core GEMM on fp32 inputs (tests only): splits A (M,K) and W (N,K) into bf16 hi|lo, runs the
 // tcgen05 kernel with the handle's precision and writes fp32 out (M,N).  Synchronous; allocates scratch.
 MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W, const float* bias, const float* R, const float* gate,
@@ -1259,7 +1377,7 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
   return 0;
 }
 
-// Times `iters` back-to-back launches of the tensor-core GEMM kernel (zero operands, pre-split, L2-warm) with CUDA
+// Times `iters` back-to-back launches of the tensor-core GEMM kernel (pseudo-random operands, pre-split, L2-warm) with CUDA
 // events on `stream`; used by bench.py for the per-kernel roofline entry.  epi as in mdtb200_debug_gemm.
 MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int epi, int iters, float* avg_us, void* stream) {
   if (!h || !avg_us || iters < 1) return MDTB200_EINVAL;
@@ -1269,7 +1387,9 @@ MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int e
   __nv_bfloat16 *a16 = nullptr, *w16 = nullptr, *c16 = nullptr; float *c = nullptr, *gate = nullptr;
   CUDA_TRY(h, cudaMalloc(&a16, Mp * 2 * K * 2)); CUDA_TRY(h, cudaMalloc(&w16, (size_t)N * 2 * K * 2));
   CUDA_TRY(h, cudaMalloc(&c16, Mp * 2 * N * 2)); CUDA_TRY(h, cudaMalloc(&c, Mp * N * 4)); CUDA_TRY(h, cudaMalloc(&gate, Mp * N * 4));
-  cudaMemsetAsync(a16, 0, Mp * 2 * K * 2, st); cudaMemsetAsync(w16, 0, (size_t)N * 2 * K * 2, st);
+  // pseudo-random, non-zero split-bf16 operands (hi ~ U(-1, 1), lo ~ 2^-9 of that), as the graph's GEMMs see them
+  fill_operand_kernel<<<(unsigned)((Mp * K + 255) / 256), 256, 0, st>>>(a16, (int64_t)Mp, K, 0x1234u);
+  fill_operand_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(w16, (int64_t)N, K, 0x9876u);
   cudaMemsetAsync(c, 0, Mp * N * 4, st); cudaMemsetAsync(gate, 0, Mp * N * 4, st);
   tc::TcGemm t{};
   t.A16 = a16; t.lda16 = 2 * K; t.W16 = w16; t.C = (epi == EPI_GELU) ? nullptr : c; t.ldc = N;

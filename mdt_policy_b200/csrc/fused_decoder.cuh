@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(FD_THREADS, 1) fused_decoder_kernel(const Fuse
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
+  pdl_wait(KT_FUSED);
 
   const int passes = P.passes;
   if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");

@@ -35,6 +35,7 @@ struct TcGemm {
   int M, N, K, epi, passes;
   unsigned long long* trace;
   int gi, go, goff;            // output-row remap (row = (m / gi) * go + goff + m % gi; gi == 0: identity), C / C16 only
+  int wg_rows, wg_stride, w_rows;   // weight groups: rows [g * wg_rows, +wg_rows) of A use W rows [g * wg_stride + n, ...) (w_rows = total W rows)
 };
 
 struct TcParams {
@@ -44,6 +45,7 @@ struct TcParams {
   int M, N, K, epi;
   unsigned long long* trace;   // optional (tests): per-CTA globaltimer stamps [cta][8]
   int gi, go, goff;
+  int wg_rows, wg_stride;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -180,6 +182,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int n0w = n0 + (p.wg_rows ? (m0 / p.wg_rows) * p.wg_stride : 0);     // W row of this tile (weight groups, e.g. one per head)
   const int nkb = p.K / BK;
   if (threadIdx.x == 0) TC_STAMP(0);
 
@@ -204,11 +207,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int kb = 0; kb < npre; ++kb) {
       const uint32_t st = sbase + kb * L::STAGE;
       mbar_expect_tx(full_bar(kb), L::STAGE);
-      tma_load_2d(st + L::A_TILE, &tmW, full_bar(kb), kb * BK, n0);                                         // W hi
-      if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(kb), p.K + kb * BK, n0);  // W lo
+      tma_load_2d(st + L::A_TILE, &tmW, full_bar(kb), kb * BK, n0w);                                         // W hi
+      if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(kb), p.K + kb * BK, n0w);  // W lo
     }
   }
-  pdl_wait();       // prologue above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_wait(KT_GEMM);       // prologue above overlapped the previous kernel's tail; its results are visible from here on
   if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
@@ -221,8 +224,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kb >= npre) {
           mbar_wait(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), L::STAGE);
-          tma_load_2d(st + L::A_TILE, &tmW, full_bar(s), kb * BK, n0);                                         // W hi
-          if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(s), p.K + kb * BK, n0);  // W lo
+          tma_load_2d(st + L::A_TILE, &tmW, full_bar(s), kb * BK, n0w);                                         // W hi
+          if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(s), p.K + kb * BK, n0w);  // W lo
         }
         tma_load_2d(st, &tmA, full_bar(s), kb * BK, m0);                                                       // A hi
         if (PASSES == 3) tma_load_2d(st + L::A_TILE + L::W_TILE, &tmA, full_bar(s), p.K + kb * BK, m0);        // A lo
@@ -375,6 +378,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 64) TC_STAMP(7);
   }
   __syncthreads();
+  ktrace(KT_GEMM, 1);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, L::TMEM_COLS);
@@ -460,13 +464,19 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   // A "widest tile that still fills ~1 wave, else narrowest" policy was 11 % slower end to end and no better for training.
   const int mt = (g.M + BM - 1) / BM;
   const bool wide = mt >= 16 && g.N % 192 == 0 && (g.N / 192) * mt <= 148 && (g.N % 128 != 0 || (g.N / 128) * mt > 148);
-  const int bn = wide ? 192 : (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
+  int bn = wide ? 192 : (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
+  {   // experiment overrides: MDTB200_BN_D (GEMMs with N < 1024), MDTB200_BN_WIDE (N >= 1024)
+    static const int ov_d = getenv("MDTB200_BN_D") ? atoi(getenv("MDTB200_BN_D")) : 0;
+    static const int ov_w = getenv("MDTB200_BN_WIDE") ? atoi(getenv("MDTB200_BN_WIDE")) : 0;
+    const int ov = g.N >= 1024 ? ov_w : ov_d;
+    if ((ov == 64 || ov == 128 || ov == 192) && g.N % ov == 0) bn = ov;
+  }
   CUtensorMap ta, tw;
   const char* e;
   if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
-  if ((e = enc.get(g.W16, g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
+  if ((e = enc.get(g.W16, g.w_rows > 0 ? g.w_rows : g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
-             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff};
+             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride};
   if (g.passes == 3) {
     if (bn == 192) launch_one<192, 3>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {

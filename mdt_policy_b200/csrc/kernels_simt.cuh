@@ -32,9 +32,29 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // Programmatic dependent launch (PDL): every kernel first lets its dependents start launching (their prologue
 // overlaps our tail), then waits until all prerequisite grids have completed and flushed before touching memory.
+// Optional in-graph kernel timeline (tools/ktrace.py, mdtb200_debug_ktrace): when armed, thread 0 of every CTA appends
+// {globaltimer, tag | event | sm id | CTAs in grid | linear block id} after its dependency wait (event 0) and, for the
+// main kernels, when it finishes (event 1).  One predictable branch on a __device__ pointer when disarmed.
+__device__ unsigned long long* g_ktrace = nullptr;
+__device__ unsigned int g_ktrace_n = 0;
+__device__ unsigned int g_ktrace_cap = 0;
+enum KTag : int { KT_OTHER = 0, KT_GEMM = 1, KT_LN = 2, KT_ATTN = 3, KT_HEAD = 4, KT_EMBED = 5, KT_CROSS = 6, KT_PACK = 7, KT_SKINNY = 8, KT_FUSED = 9 };
+__device__ __forceinline__ void ktrace(int tag, int event) {
+  if (g_ktrace != nullptr && threadIdx.x == 0) {
+    unsigned long long t; unsigned int sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    const unsigned int i = atomicAdd(&g_ktrace_n, 1u);
+    if (i < g_ktrace_cap) {
+      const unsigned long long nb = (unsigned long long)gridDim.x * gridDim.y, bi = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;
+      g_ktrace[2 * (size_t)i] = t;
+      g_ktrace[2 * (size_t)i + 1] = ((unsigned long long)tag << 56) | ((unsigned long long)event << 52) | ((unsigned long long)sm << 40) | (nb << 20) | bi;
+    }
+  }
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+__device__ __forceinline__ void pdl_wait(int tag = KT_OTHER) { asm volatile("griddepcontrol.wait;" ::: "memory"); ktrace(tag, 0); }
+__device__ __forceinline__ void pdl_enter(int tag = KT_OTHER) { pdl_trigger(); pdl_wait(tag); }
 
 // ------------------------------------------------------------------------------------------
 // activations (exact variants, matching ATen)
@@ -205,7 +225,7 @@ struct SkinnyArgs { const float* A; const float* W; const float* bias; float* C;
 
 __global__ void __launch_bounds__(256) skinny_gemm_kernel(SkinnyArgs g) {
   extern __shared__ __align__(16) float sA[];           // [M][K]
-  pdl_enter();
+  pdl_enter(KT_SKINNY);
   for (int e = threadIdx.x * 4; e < g.M * g.K; e += blockDim.x * 4) *reinterpret_cast<float4*>(sA + e) = *reinterpret_cast<const float4*>(g.A + e);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,7 +275,7 @@ struct LnArgs {
 
 template <int VPL>   // float4 vectors per lane: d = 128 * VPL
 __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
-  pdl_enter();
+  pdl_enter(KT_LN);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const float* xr = a.x + (size_t)warp * a.d;
@@ -342,7 +362,7 @@ inline size_t attention_smem_bytes(int d, int H, int Tq, int Tk) {
 
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float att_smem[];
-  pdl_enter();
+  pdl_enter(KT_ATTN);
   const int D = a.H * a.hd, DP = D + 4, Tq = a.Tq, Tk = a.Tk, hd = a.hd;
   float* sq = att_smem;
   float* sk = sq + Tq * DP;
@@ -415,7 +435,7 @@ __global__ void __launch_bounds__(128) attention_fixed_kernel(AttnArgs a) {
   __shared__ __align__(16) float sk[TK * DP];
   __shared__ __align__(16) float sv[TK * DP];
   __shared__ float sp[HC * TQ * (TK + 1)];
-  pdl_enter();
+  pdl_enter(KT_ATTN);
   const int b = blockIdx.x, c0 = blockIdx.y * DC, tid = threadIdx.x;
 #pragma unroll
   for (int e = tid; e < TQ * D4; e += NT) {
@@ -486,6 +506,244 @@ __global__ void __launch_bounds__(128) attention_fixed_kernel(AttnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Algebraic cross-attention (decoder, transformer_blocks.py:300-304 with Attention.forward :119-158).  The context K/V are
+// constant over a sampling call, so per sample b, head h and context token j
+//     score[i,h,j] = (LN3(x_i) Wq_h^T + bq_h) . k_hj / sqrt(hd) = LN3(x_i) . G_hj + c_hj ,   G_hj = Wq_h^T k_hj / sqrt(hd)  (d floats)
+//     x_i += c_proj(sum_j p_ihj v_hj) = sum_{h,j} p_ihj U_hj + b_co ,                         U_hj = Wco[:, head h] v_hj     (d floats)
+// G and U are computed ONCE per call by two head-grouped tensor-core GEMMs per layer (K = head_dim padded to 64); the per-step
+// LN3 -> query GEMM -> attention -> c_proj GEMM -> LN2 chain (5 kernels) becomes ONE kernel, cross_row_kernel.
+
+// commit time: stacked per-head weight operands (split bf16, K padded to 64):
+//   wg[(h*d + m), c] = Wq[h*hd + c, m] / sqrt(hd)        wu[(h*d + n), c] = Wco[n, h*hd + c]          (c < hd, zero beyond)
+__global__ void pack_cross_weights_kernel(const float* __restrict__ Wq, const float* __restrict__ Wco, __nv_bfloat16* __restrict__ wg,
+                                          __nv_bfloat16* __restrict__ wu, int d, int H, int hd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * d * 64) return;
+  const int c = idx % 64, m = (idx / 64) % d, h = idx / (64 * d);
+  float g = 0.f, u = 0.f;
+  if (c < hd) {
+    g = Wq[(size_t)(h * hd + c) * d + m] * (1.0f / sqrtf((float)hd));
+    u = Wco[(size_t)m * d + h * hd + c];
+  }
+  __nv_bfloat16 hi, lo;
+  const size_t o = (size_t)(h * d + m) * 128 + c;
+  split_bf16(g, hi, lo); wg[o] = hi; wg[o + 64] = lo;
+  split_bf16(u, hi, lo); wu[o] = hi; wu[o + 64] = lo;
+}
+
+// per call: head-major split-bf16 operands of the context keys / values of every decoder layer, and the score constants
+//   ka[l][(h*mcp + r), c] = k_l[r, h*hd + c]   va likewise   (r = b*Tc + j < Mc, zero padding to mcp rows and 64 columns)
+//   ctab[l][b][h*Tc + j] = bq_l[h*hd : (h+1)*hd] . k_l[b*Tc + j, h*hd : ...] / sqrt(hd)
+struct CrossPackArgs {
+  const float* kv; int ldkv;          // (Mc, L*2d): layer l keys at column l*2d, values at l*2d + d
+  const float* bq_all;                // (L, d): cross-attention query biases of every decoder layer
+  __nv_bfloat16 *ka, *va; size_t layer_stride16;   // elements between layers
+  float* ctab; size_t ctab_layer_stride;
+  int Mc, mcp, Tc, H, hd, d, L;
+};
+__global__ void __launch_bounds__(256) pack_cross_operands_kernel(CrossPackArgs a) {
+  pdl_enter(KT_PACK);
+  const int l = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (h, r, c): c < 64
+  if (idx < a.H * a.mcp * 64) {
+    const int c = idx % 64, r = (idx / 64) % a.mcp, h = idx / (64 * a.mcp);
+    float kx = 0.f, vx = 0.f;
+    if (r < a.Mc && c < a.hd) {
+      const float* row = a.kv + (size_t)r * a.ldkv + (size_t)l * 2 * a.d + h * a.hd + c;
+      kx = row[0]; vx = row[a.d];
+    }
+    __nv_bfloat16 hi, lo;
+    const size_t o = (size_t)l * a.layer_stride16 + (size_t)(h * a.mcp + r) * 128 + c;
+    split_bf16(kx, hi, lo); a.ka[o] = hi; a.ka[o + 64] = lo;
+    split_bf16(vx, hi, lo); a.va[o] = hi; a.va[o + 64] = lo;
+  }
+  if (idx < a.Mc * a.H) {            // one score constant per (row r = b*Tc + j, head h)
+    const int h = idx % a.H, r = idx / a.H, b = r / a.Tc, j = r % a.Tc;
+    const float* kr = a.kv + (size_t)r * a.ldkv + (size_t)l * 2 * a.d + h * a.hd;
+    const float* bq = a.bq_all + (size_t)l * a.d + h * a.hd;
+    float acc = 0.f;
+    for (int c = 0; c < a.hd; ++c) acc = fmaf(bq[c], kr[c], acc);
+    a.ctab[(size_t)l * a.ctab_layer_stride + (size_t)b * a.H * a.Tc + h * a.Tc + j] = acc * (1.0f / sqrtf((float)a.hd));
+  }
+}
+
+struct CrossRowArgs {
+  float* xh;                                   // (M, d) residual stream, updated in place
+  const float* gtab; const float* utab;        // this layer / this sub-batch: rows (h*mcp + b*Tc + j), d floats each
+  const float* ctab;                           // (B, H*Tc)
+  int mcp;
+  const float *ln3_w, *ln3_b, *bco, *ln2_w, *ln2_b, *shift, *scale; int mod_stride;
+  __nv_bfloat16* a16; int ld16, lo_off;        // LN2 (+modulate) output: split-bf16 operand of c_fc
+  int B, T, Tc, H, d;
+};
+constexpr int CR_THREADS = 384;
+inline size_t cross_row_smem_bytes(int d, int T, int Tc, int H) {
+  return ((size_t)(2 * T + H * Tc) * (d + 4) + (size_t)T * H * Tc + 5 * (size_t)d) * sizeof(float);
+}
+
+// One CTA per sample.  smem: z[T][d+4] (LN3 output), x[T][d+4] (residual rows), tab[H*Tc][d+4] (G, later U), p[T][H*Tc], prm[5][d]
+template <int VPL>
+__global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
+  extern __shared__ __align__(16) float cr_smem[];
+  constexpr int d = VPL * 128, DP = d + 4, D4 = d / 4;
+  const int T = a.T, Tc = a.Tc, H = a.H, HT = H * Tc;
+  float* sz = cr_smem;
+  float* sx = sz + T * DP;
+  float* stab = sx + T * DP;
+  float* sp = stab + HT * DP;
+  float* sprm = sp + T * HT;            // bco | ln2_w | ln2_b | shift | scale
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_enter(KT_CROSS);
+  // ---- 1. every global operand is requested up front: G and U rows (registers), the T residual rows + LN3 parameters (one warp
+  //         per row), the small parameter vectors (remaining warps -> shared memory)
+  constexpr int TPT = 8;                // float4 of G (and of U) per thread: H*Tc*d/4 <= 8 * 384
+  float4 g[TPT], u[TPT];
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    const int e = tid + t * CR_THREADS;
+    if (e < HT * D4) {
+      const int hj = e / D4, c = (e % D4) * 4;
+      const size_t row = (size_t)(hj / Tc) * a.mcp + (size_t)b * Tc + hj % Tc;
+      g[t] = *reinterpret_cast<const float4*>(a.gtab + row * d + c);
+      u[t] = *reinterpret_cast<const float4*>(a.utab + row * d + c);
+    }
+  }
+  float4 xr[VPL], w3[VPL], b3[VPL];
+  if (warp < T) {
+    const float* xp = a.xh + ((size_t)b * T + warp) * d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      xr[i] = *reinterpret_cast<const float4*>(xp + c);
+      w3[i] = *reinterpret_cast<const float4*>(a.ln3_w + c);
+      b3[i] = a.ln3_b ? *reinterpret_cast<const float4*>(a.ln3_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    const size_t mrow = (size_t)b * a.mod_stride;
+    for (int e = (tid - T * 32) * 4; e < 5 * d; e += (CR_THREADS - T * 32) * 4) {
+      const int which = e / d, c = e % d;
+      const float* src = which == 0 ? a.bco : which == 1 ? a.ln2_w : which == 2 ? a.ln2_b : which == 3 ? (a.shift ? a.shift + mrow : nullptr) : (a.shift ? a.scale + mrow : nullptr);
+      float4 v = src ? *reinterpret_cast<const float4*>(src + c) : (which == 4 ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+      *reinterpret_cast<float4*>(sprm + e) = v;
+    }
+  }
+  // ---- 2. G -> shared memory; LN3 of the T rows -> z, raw rows -> x
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    const int e = tid + t * CR_THREADS;
+    if (e < HT * D4) *reinterpret_cast<float4*>(stab + (e / D4) * DP + (e % D4) * 4) = g[t];
+  }
+  if (warp < T) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (xr[i].x + xr[i].y) + (xr[i].z + xr[i].w);
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float dx = xr[i].x - mean, dy = xr[i].y - mean, dz = xr[i].z - mean, dw = xr[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(sx + warp * DP + c) = xr[i];
+      *reinterpret_cast<float4*>(sz + warp * DP + c) =
+          make_float4((xr[i].x - mean) * rstd * w3[i].x + b3[i].x, (xr[i].y - mean) * rstd * w3[i].y + b3[i].y,
+                      (xr[i].z - mean) * rstd * w3[i].z + b3[i].z, (xr[i].w - mean) * rstd * w3[i].w + b3[i].w);
+    }
+  }
+  __syncthreads();
+  // ---- 3. scores: one thread per (row i, head h, context token j); causal top-left mask j <= i
+  for (int e = tid; e < T * HT; e += CR_THREADS) {
+    const int i = e / HT, hj = e % HT, j = hj % Tc;
+    float sc = -INFINITY;
+    if (j <= i) {
+      const float* zp = sz + i * DP;
+      const float* gp = stab + hj * DP;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < d; c += 8) {
+        const float4 z0 = *reinterpret_cast<const float4*>(zp + c), g0 = *reinterpret_cast<const float4*>(gp + c);
+        const float4 z1 = *reinterpret_cast<const float4*>(zp + c + 4), g1 = *reinterpret_cast<const float4*>(gp + c + 4);
+        acc0 = fmaf(z0.x, g0.x, acc0); acc0 = fmaf(z0.y, g0.y, acc0); acc0 = fmaf(z0.z, g0.z, acc0); acc0 = fmaf(z0.w, g0.w, acc0);
+        acc1 = fmaf(z1.x, g1.x, acc1); acc1 = fmaf(z1.y, g1.y, acc1); acc1 = fmaf(z1.z, g1.z, acc1); acc1 = fmaf(z1.w, g1.w, acc1);
+      }
+      sc = (acc0 + acc1) + a.ctab[(size_t)b * HT + hj];
+    }
+    sp[e] = sc;
+  }
+  __syncthreads();
+  // ---- 4. U -> shared memory (G is no longer needed); softmax over j per (row, head)
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    const int e = tid + t * CR_THREADS;
+    if (e < HT * D4) *reinterpret_cast<float4*>(stab + (e / D4) * DP + (e % D4) * 4) = u[t];
+  }
+  if (tid < T * H) {
+    float* row = sp + (tid / H) * HT + (tid % H) * Tc;
+    float mx = -INFINITY;
+    for (int j = 0; j < Tc; ++j) mx = fmaxf(mx, row[j]);
+    float sum = 0.f;
+    for (int j = 0; j < Tc; ++j) { float ex = expf(row[j] - mx); row[j] = ex; sum += ex; }
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < Tc; ++j) row[j] *= inv;
+  }
+  __syncthreads();
+  // ---- 5. x_i += sum_hj p_i,hj U_hj + b_co   (kept in shared memory for the LayerNorm below, written back to the residual stream)
+  for (int e = tid; e < T * D4; e += CR_THREADS) {
+    const int i = e / D4, c = (e % D4) * 4;
+    const float* pr = sp + i * HT;
+    float4 acc = *reinterpret_cast<const float4*>(sprm + c);
+    for (int hj = 0; hj < HT; ++hj) {
+      const float pj = pr[hj];
+      const float4 uv = *reinterpret_cast<const float4*>(stab + hj * DP + c);
+      acc.x = fmaf(pj, uv.x, acc.x); acc.y = fmaf(pj, uv.y, acc.y); acc.z = fmaf(pj, uv.z, acc.z); acc.w = fmaf(pj, uv.w, acc.w);
+    }
+    const float4 x0 = *reinterpret_cast<const float4*>(sx + i * DP + c);
+    const float4 x1 = make_float4(x0.x + acc.x, x0.y + acc.y, x0.z + acc.z, x0.w + acc.w);
+    *reinterpret_cast<float4*>(sx + i * DP + c) = x1;
+    *reinterpret_cast<float4*>(a.xh + ((size_t)b * T + i) * d + c) = x1;
+  }
+  __syncthreads();
+  // ---- 6. LN2 (+ AdaLN modulate) -> split-bf16 operand of c_fc, one warp per row
+  if (warp < T) {
+    float4 v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = *reinterpret_cast<const float4*>(sx + warp * DP + (i * 32 + lane) * 4);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+    const size_t row = (size_t)b * T + warp;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 w = *reinterpret_cast<const float4*>(sprm + d + c), bb = *reinterpret_cast<const float4*>(sprm + 2 * d + c);
+      const float4 sh = *reinterpret_cast<const float4*>(sprm + 3 * d + c), sc = *reinterpret_cast<const float4*>(sprm + 4 * d + c);
+      float o[4] = {(v[i].x - mean) * rstd * w.x, (v[i].y - mean) * rstd * w.y, (v[i].z - mean) * rstd * w.z, (v[i].w - mean) * rstd * w.w};
+      if (a.ln2_b) { o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w; }
+      if (a.shift) { o[0] = sh.x + o[0] * sc.x; o[1] = sh.y + o[1] * sc.y; o[2] = sh.z + o[2] * sc.z; o[3] = sh.w + o[3] * sc.w; }
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_bf16(o[j], hi[j], lo[j]);
+      __nv_bfloat16* ph = a.a16 + row * a.ld16 + c;
+      *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
+      *reinterpret_cast<uint2*>(ph + a.lo_off) = *reinterpret_cast<uint2*>(lo);
+    }
+  }
+  ktrace(KT_CROSS, 1);
+}
+
+// ------------------------------------------------------------------------------------------
 // Sinusoidal sigma embedding: pe[r, :] = [sin(e f_k), cos(e f_k)], e = log(sigma_r)/4,
 // f_k = exp(-k ln(10000)/(half-1))      (mdtv_transformer.py:13-25, :238-244)
 __global__ void sigma_posemb_kernel(const float* __restrict__ sigma, int R, int d, float* __restrict__ pe) {
@@ -518,7 +776,7 @@ struct ActEmbArgs {
   const float* W; const float* b; float* xh; float sigma_data; int precondition;
 };
 __global__ void action_embed_kernel(ActEmbArgs a) {
-  pdl_enter();
+  pdl_enter(KT_EMBED);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.M * a.d) return;
   int m = idx / a.d, n = idx % a.d;
@@ -560,7 +818,7 @@ struct HeadArgs {
 
 template <int VPL>
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
-  pdl_enter();
+  pdl_enter(KT_HEAD);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const float* xr = a.xh + (size_t)warp * a.d;
@@ -680,6 +938,18 @@ __global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
   int64_t r = idx / cols; int c = (int)(idx % cols);
   __nv_bfloat16 hi, lo;
   split_bf16(w[idx], hi, lo);
+  o[r * 2 * cols + c] = hi;
+  o[r * 2 * cols + cols + c] = lo;
+}
+
+// pseudo-random split-bf16 operand [rows, 2*cols] for kernel timing (hash of the element index)
+__global__ void fill_operand_kernel(__nv_bfloat16* __restrict__ o, int64_t rows, int cols, unsigned int seed) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const float v = 2.0f * hash_uniform(seed, (unsigned long long)idx) - 1.0f;
+  int64_t r = idx / cols; int c = (int)(idx % cols);
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
   o[r * 2 * cols + c] = hi;
   o[r * 2 * cols + cols + c] = lo;
 }

@@ -108,46 +108,94 @@ def _on_cuda(*tensors) -> bool:
 
 
 # --------------------------------------------------------------------------------------------------- samplers
+# Every sampler below first tries the fused CUDA path (GCDenoiser.sample -> mdtb200_sample: the whole loop is one CUDA graph).
+# Anything the graph does not cover (callbacks, scalers, churn, extra_args, the stochastic ancestral sampler, foreign models)
+# runs through ONE generic driver, `_integrate`, parameterised by a per-sampler update rule; the rules are the formulas of
+# mdt/models/edm_diffusion/gc_sampling.py (cited per rule), the signatures and callback payloads are the reference's.
+
+def _log_step(x, denoised, sigma, sigma_next):
+    """exponential-integrator step in t = -log sigma: x <- (s'/s) x - expm1(-(t' - t)) D  (DPM-Solver-1 == DDIM, :948-950)"""
+    t, t_next = -sigma.log(), -sigma_next.log()
+    return ((-t_next).exp() / (-t).exp()) * x - torch.expm1(t - t_next) * denoised
+
+
+def _rule_ddim(ctx, x, denoised, sigma, sigma_next):                       # :922-951
+    return _log_step(x, denoised, sigma, sigma_next)
+
+
+def _rule_euler(ctx, x, denoised, sigma, sigma_next):                      # :201-207
+    return x + to_d(x, sigma, denoised) * (sigma_next - sigma)
+
+
+def _rule_heun(ctx, x, denoised, sigma, sigma_next):                       # :296-309
+    d, dt = to_d(x, sigma, denoised), sigma_next - sigma
+    if sigma_next == 0:
+        return x + d * dt
+    x_mid = x + d * dt
+    d_mid = to_d(x_mid, sigma_next, ctx["eval"](x_mid, sigma_next))
+    return x + (d + d_mid) / 2 * dt
+
+
+def _rule_euler_ancestral(ctx, x, denoised, sigma, sigma_next):            # :240-251
+    sigma_down, sigma_up = get_ancestral_step(sigma, sigma_next, eta=ctx["eta"])
+    x = x + to_d(x, sigma, denoised) * (sigma_down - sigma)
+    if sigma_down > 0:
+        x = x + torch.randn_like(x) * sigma_up
+    return x
+
+
+def _rule_dpmpp_2m(ctx, x, denoised, sigma, sigma_next):                   # :716-732
+    prev, ctx["prev"] = ctx.get("prev"), (denoised, sigma)
+    if prev is None or sigma_next == 0:
+        return _log_step(x, denoised, sigma, sigma_next)
+    old_denoised, sigma_prev = prev
+    r = (sigma_prev.log() - sigma.log()) / (sigma.log() - sigma_next.log())
+    return _log_step(x, (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised, sigma, sigma_next)
+
+
+def _integrate(rule, model, state, x, goal, sigmas, scaler=None, extra_args=None, callback=None, cb_key="x", churn=None, eta=1.):
+    extra_args = {} if extra_args is None else extra_args
+    ones = x.new_ones([x.shape[0]])
+    ctx = {"eta": eta, "eval": lambda xx, sig: model(state, xx, goal, sig * ones, **extra_args)}
+    n = len(sigmas) - 1
+    for i in range(n):
+        sigma_hat = sigmas[i]
+        if churn is not None:               # Karras "churn": the reference draws eps every step, also when gamma == 0 (:195)
+            s_churn, s_tmin, s_tmax, s_noise = churn
+            gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.
+            eps = torch.randn_like(x) * s_noise
+            sigma_hat = sigmas[i] * (gamma + 1)
+            if gamma > 0:
+                x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = ctx["eval"](x, sigma_hat)
+        if callback is not None:
+            callback({cb_key: x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigma_hat, 'denoised': denoised})
+        x = rule(ctx, x, denoised, sigma_hat, sigmas[i + 1])
+        if scaler is not None:
+            x = scaler.clip_output(x)
+    return x
+
+
+def _fused(model, name, state, action, goal, sigmas, scaler, extra_args, callback):
+    if _fused_ok(model, scaler, extra_args or {}, callback) and _on_cuda(action, goal):
+        return model.sample(state, action, goal, sigmas, sampler=name)
+    return None
+
 
 @torch.no_grad()
 def sample_ddim(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.):
-    """DPM-Solver-1 / DDIM (gc_sampling.py:922-951): x <- (s'/s) x - expm1(-h) D, h = log s - log s'."""
-    extra_args = {} if extra_args is None else extra_args
-    if _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal):
-        return model.sample(state, action, goal, sigmas, sampler="ddim")
-    s_in = action.new_ones([action.shape[0]])
-    for i in range(len(sigmas) - 1):
-        denoised = model(state, action, goal, sigmas[i] * s_in, **extra_args)
-        if callback is not None:
-            callback({'action': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
-        t, t_next = sigmas[i].log().neg(), sigmas[i + 1].log().neg()
-        h = t_next - t
-        action = (t_next.neg().exp() / t.neg().exp()) * action - (-h).expm1() * denoised
-    return action
+    """DPM-Solver-1 / DDIM (gc_sampling.py:922-951)."""
+    out = _fused(model, "ddim", state, action, goal, sigmas, scaler, extra_args, callback)
+    return out if out is not None else _integrate(_rule_ddim, model, state, action, goal, sigmas, None, extra_args, callback, "action")
 
 
 @torch.no_grad()
 def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
                  s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
     """Karras Algorithm 2 without the 2nd-order correction (gc_sampling.py:164-210)."""
-    extra_args = {} if extra_args is None else extra_args
-    if s_churn == 0 and _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal):
-        return model.sample(state, action, goal, sigmas, sampler="euler")
-    s_in = action.new_ones([action.shape[0]])
-    n = len(sigmas) - 1
-    for i in range(n):
-        gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.
-        sigma_hat = sigmas[i] * (gamma + 1)
-        if gamma > 0:
-            action = action + torch.randn_like(action) * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
-        denoised = model(state, action, goal, sigma_hat * s_in, **extra_args)
-        d = to_d(action, sigma_hat, denoised)
-        if callback is not None:
-            callback({'x': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigma_hat, 'denoised': denoised})
-        action = action + d * (sigmas[i + 1] - sigma_hat)
-        if scaler is not None:
-            action = scaler.clip_output(action)
-    return action
+    out = _fused(model, "euler", state, action, goal, sigmas, scaler, extra_args, callback) if s_churn == 0 else None
+    return out if out is not None else _integrate(_rule_euler, model, state, action, goal, sigmas, scaler, extra_args, callback,
+                                                  churn=(s_churn, s_tmin, s_tmax, s_noise))
 
 
 @torch.no_grad()
@@ -155,77 +203,24 @@ def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None
                 s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
     """Karras Algorithm 2 (Heun), gc_sampling.py:256-311: Euler predictor + trapezoidal corrector, plain Euler on
     the last step (sigma_next == 0)."""
-    extra_args = {} if extra_args is None else extra_args
-    if (s_churn == 0 and _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal)
-            and float(sigmas[-1]) == 0.0 and bool((sigmas[:-1] > 0).all())):
-        return model.sample(state, action, goal, sigmas, sampler="heun")
-    s_in = action.new_ones([action.shape[0]])
-    n = len(sigmas) - 1
-    for i in range(n):
-        gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.
-        sigma_hat = sigmas[i] * (gamma + 1)
-        if gamma > 0:
-            action = action + torch.randn_like(action) * s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
-        denoised = model(state, action, goal, sigma_hat * s_in, **extra_args)
-        d = to_d(action, sigma_hat, denoised)
-        if callback is not None:
-            callback({'x': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigma_hat, 'denoised': denoised})
-        dt = sigmas[i + 1] - sigma_hat
-        if sigmas[i + 1] == 0:
-            action = action + d * dt
-        else:
-            action_2 = action + d * dt
-            denoised_2 = model(state, action_2, goal, sigmas[i + 1] * s_in, **extra_args)
-            d_2 = to_d(action_2, sigmas[i + 1], denoised_2)
-            action = action + (d + d_2) / 2 * dt
-        if scaler is not None:
-            action = scaler.clip_output(action)
-    return action
+    graph_ok = s_churn == 0 and float(sigmas[-1]) == 0.0 and bool((sigmas[:-1] > 0).all())
+    out = _fused(model, "heun", state, action, goal, sigmas, scaler, extra_args, callback) if graph_ok else None
+    return out if out is not None else _integrate(_rule_heun, model, state, action, goal, sigmas, scaler, extra_args, callback,
+                                                  churn=(s_churn, s_tmin, s_tmax, s_noise))
 
 
 @torch.no_grad()
 def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
                            disable=None, eta=1.):
-    """gc_sampling.py:213-253 (stochastic: always the generic loop, noise drawn by torch per step)."""
-    extra_args = {} if extra_args is None else extra_args
-    s_in = action.new_ones([action.shape[0]])
-    for i in range(len(sigmas) - 1):
-        denoised = model(state, action, goal, sigmas[i] * s_in, **extra_args)
-        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
-        if callback is not None:
-            callback({'x': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
-        d = to_d(action, sigmas[i], denoised)
-        action = action + d * (sigma_down - sigmas[i])
-        if sigma_down > 0:
-            action = action + torch.randn_like(action) * sigma_up
-        if scaler is not None:
-            action = scaler.clip_output(action)
-    return action
+    """gc_sampling.py:213-253 (stochastic: the noise of every step comes from torch's generator, as in the reference)."""
+    return _integrate(_rule_euler_ancestral, model, state, action, goal, sigmas, scaler, extra_args, callback, eta=eta)
 
 
 @torch.no_grad()
 def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
     """DPM-Solver++(2M), gc_sampling.py:699-733."""
-    extra_args = {} if extra_args is None else extra_args
-    if _fused_ok(model, scaler, extra_args, callback) and _on_cuda(action, goal):
-        return model.sample(state, action, goal, sigmas, sampler="dpmpp_2m")
-    s_in = action.new_ones([action.shape[0]])
-    old_denoised = None
-    for i in range(len(sigmas) - 1):
-        denoised = model(state, action, goal, sigmas[i] * s_in, **extra_args)
-        if callback is not None:
-            callback({'action': action, 'i': i, 'sigma': sigmas[i], 'sigma_hat': sigmas[i], 'denoised': denoised})
-        t, t_next = sigmas[i].log().neg(), sigmas[i + 1].log().neg()
-        h = t_next - t
-        ratio = t_next.neg().exp() / t.neg().exp()
-        if old_denoised is None or sigmas[i + 1] == 0:
-            action = ratio * action - (-h).expm1() * denoised
-        else:
-            r = (t - sigmas[i - 1].log().neg()) / h
-            blend = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised
-            action = ratio * action - (-h).expm1() * blend
-        old_denoised = denoised
-    return action
+    out = _fused(model, "dpmpp_2m", state, action, goal, sigmas, scaler, extra_args, callback)
+    return out if out is not None else _integrate(_rule_dpmpp_2m, model, state, action, goal, sigmas, None, extra_args, callback, "action")
 
 
 SAMPLERS = {

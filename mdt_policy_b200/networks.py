@@ -171,15 +171,18 @@ class _Engine:
             slots = self._slots = uniq
         # cheap per-call check first (the e2e path pays for every microsecond here): identity and version counters of the live
         # Parameter objects; storage moves (.to(), .cuda()) mark the module dirty through _ScoreNetBase._apply
+        # (id, version counter and storage address: `p.data = t` keeps id and version but moves the address).  What this cannot see
+        # is an in-place write THROUGH `.data` / `.detach()` views (`p.data.copy_(ema)`): those bump no counter by design -- callers
+        # doing that must call `model.invalidate_weights()`.
         quick = 0
         for _, d, leaf in slots:
             p = d[leaf]
-            quick += id(p) + p._version
+            quick += id(p) + p._version + p.data_ptr()
         if quick == self.__dict__.get("_quick_key") and not owner.__dict__.get("_weights_dirty", True):
             return
         params = [(full, d[leaf]) for full, d, leaf in slots]
         key = tuple([(p.data_ptr(), p._version) for _, p in params])
-        if key == self.weights_key:
+        if key == self.weights_key and not owner.__dict__.get("_weights_force", False):
             self._quick_key = quick
             owner.__dict__["_weights_dirty"] = False
             return
@@ -194,6 +197,7 @@ class _Engine:
         self.weights_key = key
         self._quick_key = quick
         owner.__dict__["_weights_dirty"] = False
+        owner.__dict__["_weights_force"] = False
 
     def launch_count(self) -> int:
         return int(self.lib.mdtb200_launch_count(self.handle))
@@ -250,6 +254,20 @@ class _ScoreNetBase(nn.Module):
             engines[dev] = eng
         eng.sync_weights(self)
         return eng
+
+    def invalidate_weights(self):
+        """Forces the next call to re-pack the weights into the CUDA library.  Needed only after in-place writes through
+        ``param.data`` / ``param.detach()`` (e.g. ``p.data.copy_(ema_p)``), which PyTorch does not version; ``load_state_dict``,
+        optimizer steps, ``.to()`` and ``param.data = tensor`` are detected automatically."""
+        self.__dict__["_weights_dirty"] = True
+        self.__dict__["_weights_force"] = True
+
+    def __getstate__(self):
+        # engines hold ctypes handles of the CUDA library: never copied / pickled -- a copy builds its own handle lazily
+        state = self.__dict__.copy()
+        state.pop("_engines", None)
+        state["_weights_dirty"] = True
+        return state
 
     def get_block_size(self):
         return self.block_size

@@ -12,8 +12,11 @@ from mdt_policy_b200 import gc_sampling as gcs  # noqa: E402
 from mdt_policy_b200.synthetic import synthetic_inputs  # noqa: E402
 
 
-def run(fused, B, n_dec, n_steps, sampler="ddim", bufs=("qkv", "q", "xh", "x")):
-    os.environ["MDTB200_FUSED"] = "1" if fused else "0"
+def run(fused, B, n_dec, n_steps, sampler="ddim", bufs=("qkv", "xh", "x")):
+    # reference = per-kernel path without the algebraic cross-attention; candidate chosen by DEBUG_MODE (fused | cross)
+    mode = os.environ.get("DEBUG_MODE", "cross")
+    os.environ["MDTB200_FUSED"] = "1" if (fused and mode == "fused") else "0"
+    os.environ["MDTB200_CROSS_FUSED"] = "1" if (fused and mode == "cross") else "0"
     model = H.build_product(H.mdtv_inner_cfg(2, n_dec, precision="bf16x3", ), 3, "trained")
     model.inner_model.max_batch = max(B, 16)
     inp = {k: v.cuda() for k, v in synthetic_inputs(B, seed=4).items()}
