@@ -174,6 +174,14 @@ MDTB200_API int mdtb200_op_gate_res(const float* x, const float* f, const float*
 MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const float* gate, float* df, float* prod, int M, int d,
                                         int rows_per_group, void* stream);
 
+/* Fused multi-tensor AdamW + EMA: one launch updates every parameter tensor of an optimizer group (torch.optim.AdamW's update
+ * followed by the EMA callback's ema -= (1 - decay) (ema - w), mdt/callbacks/ema.py:117-126).  table: device array of
+ * {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; float* ema; int64_t numel; float step_size; float bc2_sqrt}
+ * (step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t), t = that parameter's step count); blocks: device array of
+ * int32 pairs {tensor index, 4096-element chunk index}, one per CUDA block. */
+MDTB200_API int mdtb200_op_adamw_ema(const void* table, const void* blocks, int n_blocks, float lr, float beta1, float beta2, float eps,
+                                     float weight_decay, float ema_decay, int has_ema, void* stream);
+
 /* Kernel timeline of everything the library launches (debugging / profiling aid, tools/ktrace.py): capacity > 0 arms the
  * trace, capacity == 0 copies up to max_records {globaltimer ns, tag|event|sm|grid|block} pairs to dst_host and disarms. */
 MDTB200_API int64_t mdtb200_debug_ktrace(MdtHandle* h, int64_t capacity, unsigned long long* dst_host, int64_t max_records);

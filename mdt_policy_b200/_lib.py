@@ -22,7 +22,7 @@ EXPORTS = [
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
     "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time", "mdtb200_debug_ktrace",
     "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
-    "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout",
+    "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout", "mdtb200_op_adamw_ema",
 ]
 
 
@@ -88,6 +88,8 @@ def _declare(lib):
     lib.mdtb200_op_dropout.argtypes = [fp, fp, i64, C.c_float, C.c_uint64, vp]
     lib.mdtb200_op_gate_res.argtypes = [fp, fp, fp, fp, i32, i32, i32, vp]
     lib.mdtb200_op_gate_res_bwd.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, vp]
+    lib.mdtb200_op_adamw_ema.argtypes = [vp, vp, i32] + [C.c_float] * 6 + [i32, vp]
+    lib.mdtb200_op_adamw_ema.restype = i32
     for _n in ("gemm", "group_sum", "colsum", "act", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "gate_res", "gate_res_bwd", "dropout"):
         getattr(lib, "mdtb200_op_" + _n).restype = i32
     return lib

@@ -19,8 +19,10 @@ from . import utils
 class DenoiseAgent:
     def __init__(self, model, device="cuda", act_window_size=10, action_dim=7, num_sampling_steps=10,
                  sampler_type="ddim", noise_scheduler="exponential", sigma_data=0.5, sigma_min=0.001, sigma_max=80.0,
-                 sigma_sample_density_type="loglogistic"):
+                 sigma_sample_density_type="loglogistic", multistep=10):
         self.model = model
+        self.multistep = multistep
+        self.reset()
         self.device = torch.device(device)
         self.act_window_size = act_window_size
         self.action_dim = action_dim
@@ -29,6 +31,34 @@ class DenoiseAgent:
         self.noise_scheduler = noise_scheduler
         self.sigma_data, self.sigma_min, self.sigma_max = sigma_data, sigma_min, sigma_max
         self.sigma_sample_density_type = sigma_sample_density_type
+
+    # mdtv_agent.py:680-686
+    def reset(self):
+        """Call at the beginning of a new rollout."""
+        self.plan = None
+        self.latent_goal = None
+        self.rollout_step_counter = 0
+        self.pred_action_seq = None
+
+    # mdtv_agent.py:688-719 -- the part after the (out-of-scope) language / Voltron encoders: the caller passes their outputs
+    def forward(self, perceptual_emb, latent_goal):
+        if isinstance(perceptual_emb, dict) and "modality" not in perceptual_emb:
+            perceptual_emb = dict(perceptual_emb, modality="lang")
+        return self.denoise_actions(torch.zeros_like(latent_goal), perceptual_emb, latent_goal, inference=True)
+
+    __call__ = forward
+
+    # mdtv_agent.py:721-746 -- action chunking: a new action sequence every `multistep` calls, cached actions in between
+    def step(self, perceptual_emb, latent_goal):
+        if self.rollout_step_counter % self.multistep == 0:
+            self.pred_action_seq = self(perceptual_emb, latent_goal)
+        current_action = self.pred_action_seq[0, self.rollout_step_counter]
+        if current_action.dim() == 2:
+            current_action = current_action[:, None, :]
+        self.rollout_step_counter += 1
+        if self.rollout_step_counter == self.multistep:
+            self.rollout_step_counter = 0
+        return current_action
 
     # mdtv_agent.py:660-678 (memoised: the schedule only depends on the sampler knobs, which stay plain attributes)
     def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):

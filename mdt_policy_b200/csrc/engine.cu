@@ -1352,6 +1352,7 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
     t.A16 = g.A16; t.lda16 = g.lda16; t.W16 = g.W16; t.bias = g.bias; t.C = g.C; t.ldc = g.ldc; t.C16 = g.C16; t.ldc16 = g.ldc16; t.lo_off = g.lo_off;
     t.R = g.R; t.ldr = g.ldr; t.gate = g.gate; t.gate_stride = g.gate_stride; t.rows_per_group = g.rows_per_group;
     t.M = M; t.N = N; t.K = K; t.epi = epi; t.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1; t.trace = trace;
+    t.w_dynamic = 1;     // W was split by the kernel launched just before
     const char* em = tc::launch_tc_gemm(h->tma, t, st);
     if (em) rc = fail(h, MDTB200_ECUDA, "tcgen05 gemm: %s", em);
   }

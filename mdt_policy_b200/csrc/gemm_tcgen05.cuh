@@ -36,6 +36,7 @@ struct TcGemm {
   unsigned long long* trace;
   int gi, go, goff;            // output-row remap (row = (m / gi) * go + goff + m % gi; gi == 0: identity), C / C16 only
   int wg_rows, wg_stride, w_rows;   // weight groups: rows [g * wg_rows, +wg_rows) of A use W rows [g * wg_stride + n, ...) (w_rows = total W rows)
+  int w_dynamic;                    // 1: W is written by the preceding kernel on the stream (training ops): no W prefetch ahead of the PDL wait
 };
 
 struct TcParams {
@@ -46,6 +47,7 @@ struct TcParams {
   unsigned long long* trace;   // optional (tests): per-CTA globaltimer stamps [cta][8]
   int gi, go, goff;
   int wg_rows, wg_stride;
+  int w_early;                 // 1: W is static (inference weights): its first tiles may be requested before the dependency wait
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -157,6 +159,7 @@ struct SmemLayout {
   static constexpr int A_TILE = BM * BK * 2;                 // 16 KB
   static constexpr int W_TILE = BN * BK * 2;
   static constexpr int STAGE = (PASSES == 3 ? 2 : 1) * (A_TILE + W_TILE);
+  static constexpr int NT = THREADS;
   // one CTA per SM with the deepest ring that fits: the operand stream is bound by per-SM ingest (~100 GB/s/SM measured), and
   // 2-stage / 2-CTA-per-SM variants measured 9 % slower end to end (profiles/r01_experiments.md)
   static constexpr int STAGES = (PASSES == 3) ? (BN == 192 ? 2 : BN == 128 ? 3 : 4) : (BN == 192 ? 4 : BN == 128 ? 5 : 6);
@@ -168,9 +171,10 @@ struct SmemLayout {
 
 // ------------------------------------------------------------------------------------------ the kernel
 template <int BN, int PASSES>
-__global__ void __launch_bounds__(THREADS, SmemLayout<BN, PASSES>::MIN_CTAS)
+__global__ void __launch_bounds__((SmemLayout<BN, PASSES>::NT), (SmemLayout<BN, PASSES>::MIN_CTAS))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   using L = SmemLayout<BN, PASSES>;
+  constexpr int NT = L::NT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -202,7 +206,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   // The weight tiles do not depend on the previous kernel: the producer requests them for the first ring pass BEFORE the
   // dependency wait, so that under PDL they stream in while the predecessor is still draining its epilogue.
-  const int npre = nkb < L::STAGES ? nkb : L::STAGES;
+  const int npre = p.w_early ? (nkb < L::STAGES ? nkb : L::STAGES) : 0;
   if (warp == 0 && lane == 0) {
     for (int kb = 0; kb < npre; ++kb) {
       const uint32_t st = sbase + kb * L::STAGE;
@@ -266,9 +270,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== epilogue: TMEM -> registers -> global, by ALL 16 warps =====
     // warp w may only touch TMEM lanes [32 (w % 4), +32): the four warps of a lane quarter split the BN columns.
     const int q = warp & 3, grp = warp >> 2;
-    constexpr int CPW = BN / (THREADS / 128);            // columns per warp: 32 (BN = 128) or 16 (BN = 64)
+    constexpr int CPW = BN / (NT / 128);            // columns per warp: 32 (BN = 128) or 16 (BN = 64)
     constexpr int GPR = BN / 8;                            // 8-column groups per row (phase B work items)
-    constexpr int ITEMS = BM * GPR / THREADS;              // phase-B items per thread: 2 (BN = 64) or 4 (BN = 128)
+    constexpr int ITEMS = BM * GPR / NT;              // phase-B items per thread: 2 (BN = 64) or 4 (BN = 128)
     // residual / gate operands of phase B are fetched now, while the mainloop is still running (this hides their L2
     // latency, ~1 us); only the BN = 64 instantiation does it, the N >= 1024 GEMMs have no residual epilogue
     float4 pre_r[BN == 64 ? ITEMS * 2 : 1], pre_g[BN == 64 ? ITEMS * 2 : 1];
@@ -276,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (BN == 64 && prefetched) {
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
-        const int idx = threadIdx.x + it * THREADS;
+        const int idx = threadIdx.x + it * NT;
         const int r = idx / GPR, cg = (idx % GPR) * 8, row = m0 + r;
         if (row < p.M) {
           const float* rr = p.R + (size_t)row * p.ldr + n0 + cg;
@@ -327,7 +331,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // phase B (coalesced): consecutive threads own consecutive 8-column groups of a row -> full-line global loads/stores
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-      const int idx = threadIdx.x + it * THREADS;
+      const int idx = threadIdx.x + it * NT;
       const int r = idx / GPR, cg = (idx % GPR) * 8;
       const int row = m0 + r;
       if (row >= p.M) continue;
@@ -476,7 +480,7 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
   if ((e = enc.get(g.W16, g.w_rows > 0 ? g.w_rows : g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
-             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride};
+             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride, g.w_dynamic ? 0 : 1};
   if (g.passes == 3) {
     if (bn == 192) launch_one<192, 3>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {

@@ -357,4 +357,47 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(AttnBwdArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused multi-tensor AdamW + EMA (training step tail).  torch.optim.AdamW's single-tensor update (decoupled weight decay,
+// bias-corrected moments) and the reference's EMA callback (mdt/callbacks/ema.py:117-126: ema -= (1 - decay) (ema - w)) for ALL
+// parameter tensors of a group in ONE launch: the host passes a table of {param, grad, exp_avg, exp_avg_sq, ema, numel} and a
+// block -> (tensor, chunk) map; every block updates one 4096-element chunk.
+struct AdamTensor { float* p; const float* g; float* m; float* v; float* ema; long long n; float step_size; float bc2_sqrt; };   // 56 bytes
+struct AdamHyper { float lr, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, ema_decay; int has_ema; };   // step_size / bc2_sqrt: per tensor
+constexpr int ADAM_CHUNK = 4096;
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float* ema, const AdamHyper& h) {
+  p *= 1.0f - h.lr * h.weight_decay;                    // param.mul_(1 - lr * wd)
+  m = m + (1.0f - h.beta1) * (g - m);                   // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * h.beta2 + (1.0f - h.beta2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+  p = p - h.step_size * (m / denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
+  if (ema) { float e = *ema; e -= (1.0f - h.ema_decay) * (e - p); *ema = e; }
+}
+
+__global__ void __launch_bounds__(256) adamw_ema_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ blocks, AdamHyper h) {
+  const int2 bc = blocks[blockIdx.x];
+  const AdamTensor t = tab[bc.x];
+  h.step_size = t.step_size; h.bc2_sqrt = t.bc2_sqrt;      // torch.optim.AdamW counts steps per parameter
+  const long long base = (long long)bc.y * ADAM_CHUNK;
+  const long long end = base + ADAM_CHUNK < t.n ? base + ADAM_CHUNK : t.n;
+  const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) | reinterpret_cast<uintptr_t>(t.m) |
+                     reinterpret_cast<uintptr_t>(t.v) | (h.has_ema ? reinterpret_cast<uintptr_t>(t.ema) : 0)) & 15) == 0;
+  if (vec) {
+    const long long end4 = base + ((end - base) & ~3LL);
+    for (long long i = base + threadIdx.x * 4; i < end4; i += 256 * 4) {
+      float4 p = *reinterpret_cast<float4*>(t.p + i), m = *reinterpret_cast<float4*>(t.m + i), v = *reinterpret_cast<float4*>(t.v + i);
+      const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+      float4 e = h.has_ema ? *reinterpret_cast<float4*>(t.ema + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      adam_update(p.x, g.x, m.x, v.x, h.has_ema ? &e.x : nullptr, h); adam_update(p.y, g.y, m.y, v.y, h.has_ema ? &e.y : nullptr, h);
+      adam_update(p.z, g.z, m.z, v.z, h.has_ema ? &e.z : nullptr, h); adam_update(p.w, g.w, m.w, v.w, h.has_ema ? &e.w : nullptr, h);
+      *reinterpret_cast<float4*>(t.p + i) = p; *reinterpret_cast<float4*>(t.m + i) = m; *reinterpret_cast<float4*>(t.v + i) = v;
+      if (h.has_ema) *reinterpret_cast<float4*>(t.ema + i) = e;
+    }
+    for (long long i = end4 + threadIdx.x; i < end; i += 256) adam_update(t.p[i], t.g[i], t.m[i], t.v[i], h.has_ema ? t.ema + i : nullptr, h);
+  } else {
+    for (long long i = base + threadIdx.x; i < end; i += 256) adam_update(t.p[i], t.g[i], t.m[i], t.v[i], h.has_ema ? t.ema + i : nullptr, h);
+  }
+}
+
 }  // namespace mdt

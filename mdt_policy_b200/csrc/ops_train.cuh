@@ -101,6 +101,7 @@ MDTB200_API int mdtb200_op_gemm_tc(int mode, const float* A, const float* B, con
   __nv_bfloat16* s16 = reinterpret_cast<__nv_bfloat16*>(scratch);
   tc::TcGemm t{};
   t.bias = bias; t.C = C; t.rows_per_group = 1; t.epi = EPI_NONE; t.passes = 3;
+  t.w_dynamic = 1;      // both operands are produced by the split kernels right before the GEMM on this stream
   const int64_t Mp = (M + 127) / 128 * 128;
   if (mode == 0) {          // y[M,N] = x[M,K] W[N,K]^T
     if (K % 64 || N % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm_tc: forward needs K, N multiples of 64");
@@ -249,6 +250,17 @@ MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const
   const long n = (long)M * d;
   gate_res_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, f, gate, df, prod, M, d, rows_per_group);
   return op_check("gate_res_bwd_kernel");
+}
+
+// Fused multi-tensor AdamW (+ EMA) step: `table` = device array of AdamTensor records (56 bytes: param, grad, exp_avg, exp_avg_sq,
+// ema pointers, int64 numel, float step_size = lr / (1 - beta1^t), float bc2_sqrt = sqrt(1 - beta2^t) with t the PER-PARAMETER step
+// count, as torch.optim.AdamW keeps it), `blocks` = device array of n_blocks int2 {tensor index, 4096-element chunk index}.
+MDTB200_API int mdtb200_op_adamw_ema(const void* table, const void* blocks, int n_blocks, float lr, float beta1, float beta2, float eps,
+                                     float weight_decay, float ema_decay, int has_ema, void* stream) {
+  if (!table || !blocks || n_blocks < 1) return op_fail(MDTB200_EINVAL, "op_adamw_ema: bad argument");
+  AdamHyper h{lr, beta1, beta2, eps, weight_decay, 0.f, 1.f, ema_decay, has_ema};
+  adamw_ema_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const AdamTensor*>(table), static_cast<const int2*>(blocks), h);
+  return op_check("adamw_ema_kernel");
 }
 
 }  // extern "C"

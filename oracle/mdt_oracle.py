@@ -68,8 +68,8 @@ def _attention(P, pre, n_heads, x, kv_src, mask_mode):
     v = F.linear(kv_src, P[pre + "value.weight"], P[pre + "value.bias"]).view(B, Tk, n_heads, hd).transpose(1, 2)
     mask = None
     if mask_mode == "causal":
-        i = torch.arange(Tq).view(Tq, 1)
-        j = torch.arange(Tk).view(1, Tk)
+        i = torch.arange(Tq, device=x.device).view(Tq, 1)
+        j = torch.arange(Tk, device=x.device).view(1, Tk)
         mask = j <= i
     y = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)  # scale 1/sqrt(hd)
     y = y.transpose(1, 2).reshape(B, Tq, C)
@@ -152,7 +152,7 @@ def sigma_embedding(P, cfg: OracleCfg, sigma):
     p = cfg.prefix
     e = sigma.log() / 4
     half = cfg.embed_dim // 2
-    f = torch.exp(torch.arange(half, dtype=e.dtype) * -(math.log(10000) / (half - 1)))
+    f = torch.exp(torch.arange(half, dtype=e.dtype, device=e.device) * -(math.log(10000) / (half - 1)))
     ang = e[:, None] * f[None, :]
     pe = torch.cat((ang.sin(), ang.cos()), dim=-1)
     h = F.mish(F.linear(pe, P[p + "sigma_emb.1.weight"], P[p + "sigma_emb.1.bias"]))

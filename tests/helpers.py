@@ -74,3 +74,30 @@ def build_product(inner_cfg, seed, profile, device="cuda"):
     sd = synthetic_state_dict([(n, p.shape) for n, p in model.named_parameters()], seed, profile)
     model.load_state_dict(sd, strict=True)
     return model.to(device).eval()
+
+
+def perceiver_shapes(depth, n_lat, d=384, inner=512, n_time=1):
+    """(name, shape) list of the reference PerceiverResampler (perceiver_resampler.py:86-117), in registration order."""
+    s = [("latents", (n_lat, d)), ("time_pos_emb", (n_time, 1, d))]
+    for l in range(depth):
+        p = f"layers.{l}."
+        s += [(p + "0.norm_media.weight", (d,)), (p + "0.norm_media.bias", (d,)), (p + "0.norm_latents.weight", (d,)),
+              (p + "0.norm_latents.bias", (d,)), (p + "0.to_q.weight", (inner, d)), (p + "0.to_k.weight", (inner, d)),
+              (p + "0.to_v.weight", (inner, d)), (p + "0.to_out.weight", (d, inner)), (p + "1.0.weight", (d,)), (p + "1.0.bias", (d,)),
+              (p + "1.1.weight", (4 * d, d)), (p + "1.3.weight", (d, 4 * d))]
+    return s + [("norm.weight", (d,)), ("norm.bias", (d,))]
+
+
+def perceiver_state(named_shapes, seed):
+    """synthetic 'trained' PerceiverResampler weights: LayerNorms ~ 1 + N(0, 0.1^2) / N(0, 0.1^2), latents and time embedding
+    ~ N(0, 1) (their reference initialisation), projections ~ N(0, 1/fan_in)."""
+    from mdt_policy_b200.synthetic import synthetic_tensor
+    out = {}
+    for n, shp in named_shapes:
+        if n in ("latents", "time_pos_emb"):
+            out[n] = synthetic_tensor(n, shp, seed, "init") * 50.0
+        elif "norm" in n or ".1.0." in n:
+            out[n] = synthetic_tensor("p." + n.replace("norm", "ln_norm").replace(".1.0.", ".1.ln_0."), shp, seed, "trained")
+        else:
+            out[n] = synthetic_tensor(n, shp, seed, "trained")
+    return out

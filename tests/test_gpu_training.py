@@ -268,3 +268,34 @@ def test_training_with_shipped_dropout_probabilities():
     model.train()
     mean_l = sum(run(s)[0] for s in range(3, 9)) / 6
     assert 0.3 * l_eval < mean_l < 3.0 * l_eval
+
+
+def test_back_to_back_steps_without_host_sync_match_synchronised_steps():
+    """Regression (round 2): the tensor-core GEMM requested its W tiles ahead of the programmatic-dependent-launch wait, which is
+    only valid for static inference weights -- in the training ops W is written by the split kernel launched right before, so
+    un-synchronised training steps could read it early (timing-dependent NaNs).  Dropout off exposes it fastest (fewer kernels)."""
+    import math
+    from mdt_policy_b200 import utils as U
+
+    def run(sync):
+        model = H.build_product(H.mdtv_inner_cfg(4, 4, attn_pdrop=0.0, resid_pdrop=0.0, mlp_pdrop=0.0, max_batch=512), 12, "trained").train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=0.05)
+        inp = {k: v.cuda() for k, v in synthetic_inputs(512, seed=31).items()}
+        torch.manual_seed(0)
+        sig = U.rand_log_logistic((512,), loc=math.log(0.5), scale=0.5, min_value=0.001, max_value=80.0).cuda()
+        state = {"state_images": inp["state_images"], "modality": "lang"}
+        losses = []
+        for _ in range(8):
+            opt.zero_grad(set_to_none=True)
+            loss, _ = model.loss(state, inp["actions"], inp["goal"], inp["noise"], sig)
+            loss.backward()
+            opt.step()
+            losses.append(loss.detach())
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return torch.stack(losses).cpu()
+
+    a, b = run(True), run(False)
+    assert torch.isfinite(b).all(), b
+    assert torch.equal(a, b), (a, b)
