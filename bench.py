@@ -155,6 +155,31 @@ def cpu_reference_run(enc, dec, B, steps, warmup, budget_s=150.0):
     return value, desc, total / steps * 1e3
 
 
+def perceiver_measure(dev, B):
+    """the PerceiverResampler that produces the denoiser's 3 state tokens from the (B, 1, 392, 384) Voltron token
+    sequence (shipped config: depth 6, 8 heads x 64) -- per-chunk latency next to the sampling call it precedes."""
+    from mdt_policy_b200.perceiver import PerceiverResampler
+    m = PerceiverResampler(dim=384, depth=6, dim_head=64, heads=8, num_latents=3, num_time_embeds=1, max_batch=B).to(dev)
+    x = torch.randn(B, 1, 392, 384, device=dev)
+    for _ in range(3):
+        m(x)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = m.launch_count()
+    k = 10
+    s.record()
+    for _ in range(k):
+        m(x)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / k
+    # algorithmic FLOPs of the REFERENCE formulation per sample and layer: K/V projections of 395 tokens, q, scores, PV, to_out, FF
+    d, I, F, Q = 384, 512, 392, 3
+    per_layer = 2 * (2 * (F + Q) * d * I + Q * d * I + 2 * Q * (F + Q) * I + Q * I * d + 2 * Q * d * 4 * d)
+    return {"workload": f"PerceiverResampler depth 6, B={B}, 392 feature tokens -> 3 latents (random weights / inputs)", "ms_per_call": ms,
+            "launches_per_call": (m.launch_count() - l0) // k, "reference_formulation_gflop": 6 * per_layer * B / 1e9,
+            "note": "queries are projected into feature space, so ~21x fewer FLOPs are executed than the reference formulation counts"}
+
+
 def train_measure(args, dev, B=512, steps=10, warmup=3):
     """BASELINE config 3 on one GPU as a sub-record of the default line: diffusion loss forward + backward + optimizer step (the
     fused multi-tensor AdamW + EMA kernel of this repo) at batch B, shipped dropout probabilities, synthetic batch."""
@@ -199,10 +224,36 @@ def train_measure(args, dev, B=512, steps=10, warmup=3):
     ms = s.elapsed_time(e) / steps
     fwd_flops = B * (F_ENC * enc / 4 + F_KV * dec / 4 + (F_CORE - 107_520) * dec / 4 + 107_520 + 1_179_648 + 1_769_472 * dec)
     peak = measured_peak_tflops()[0]
-    return {"workload": f"configs[2]: training step, batch={B}, MDT-V {enc}enc+{dec}dec, diffusion loss fwd+bwd+optimizer, dropout 0.3/0.1/0.05",
-            "metric": "training action-tokens/sec", "value": B * 10 / (ms / 1e3), "unit": "action-tokens/s", "ms_per_step": ms, "steps": steps,
-            "optimizer": opt_name, "loss_first": first, "loss_last": float(last),
-            "roofline_frac": 3 * fwd_flops / (ms / 1e3) / 1e12 / peak, "exposed_comm_ms": 0.0}
+    rec = {"workload": f"configs[2]: training step, batch={B}, MDT-V {enc}enc+{dec}dec, diffusion loss fwd+bwd+optimizer, dropout 0.3/0.1/0.05",
+           "metric": "training action-tokens/sec", "unit": "action-tokens/s", "steps": steps, "optimizer": opt_name,
+           "eager": {"value": B * 10 / (ms / 1e3), "ms_per_step": ms, "loss_first": first, "loss_last": float(last)}, "exposed_comm_ms": 0.0}
+    best = ms
+    try:    # the same step replayed as ONE CUDA graph (forward + backward + fused AdamW/EMA; fresh dropout masks through the device RNG epoch)
+        from mdt_policy_b200.optim import FusedAdamWEMA, GraphedTrainStep
+        model2 = GCDenoiser(cfgd, sigma_data=0.5)
+        model2.load_state_dict(synthetic_state_dict([(n, p.shape) for n, p in model2.named_parameters()], 12, "trained"))
+        model2 = model2.to(dev).train()
+        opt2 = FusedAdamWEMA(model2.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.999, capturable=True)
+        args_ = (batch["state_images"], batch["goal"], batch["actions"], batch["noise"], sig)
+        gstep = GraphedTrainStep(model2, opt2, *args_)
+        l0 = float(gstep(*args_))
+        for _ in range(warmup):
+            gstep(*args_)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(steps):
+            lg = gstep(*args_)
+        e.record(); torch.cuda.synchronize()
+        gms = s.elapsed_time(e) / steps
+        gstep.close()
+        rec["graphed"] = {"value": B * 10 / (gms / 1e3), "ms_per_step": gms, "loss_first": l0, "loss_last": float(lg),
+                          "what": "GraphedTrainStep: one CUDA graph replay per step (inputs copied into static buffers inside the timed region)"}
+        best = min(best, gms)
+    except Exception as ex:  # noqa: BLE001
+        rec["graphed"] = {"error": repr(ex)[:300]}
+    rec["value"], rec["ms_per_step"] = B * 10 / (best / 1e3), best
+    rec["roofline_frac"] = 3 * fwd_flops / (best / 1e3) / 1e12 / peak
+    return rec
 
 
 def train_main(args):
@@ -584,7 +635,7 @@ def main():
             line["dominant_kernel"] = {"error": repr(e)}
     if world == 1:
         for name, fn in (("variant_6x6", lambda: variant_6x6(args, dev, B)), ("gpu_torch_baseline", lambda: gpu_torch_baseline(enc, dec, B, dev)),
-                         ("train", lambda: train_measure(args, dev, 512, 10, 3))):
+                         ("train", lambda: train_measure(args, dev, 512, 10, 3)), ("perceiver", lambda: perceiver_measure(dev, B))):
             if os.environ.get("MDTB200_BENCH_SKIP_EXTRAS"):
                 break
             try:

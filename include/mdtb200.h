@@ -18,10 +18,13 @@
  *   - input/output pointers are borrowed for the duration of the call only.  Weight pointers
  *     are read by mdtb200_commit_weights() and not retained: the library keeps its own packed
  *     copy (re-commit after load_state_dict / EMA swap / optimizer step).
- *   - a handle is bound to the CUDA device that was current at mdtb200_create(); it is
- *     re-entrant per handle, holds no global mutable state, and launches all work on the
- *     stream passed in (sampling graphs are captured on a private stream and *launched* on
- *     the caller's stream, so the legacy default stream is fine).
+ *   - a handle is bound to the CUDA device that was current at mdtb200_create() and holds no
+ *     global mutable state.  It owns ONE static workspace: calls on the same handle must be
+ *     ordered (one host thread at a time, and stream-ordered on the device -- issue them on one
+ *     stream, or synchronise between streams); use one handle per concurrent stream / thread.
+ *     All work is launched on the stream passed in (sampling graphs are captured on a private
+ *     stream and *launched* on the caller's stream, so the legacy default stream is fine).
+ *     The graph cache is bounded (16 entries, least recently used evicted).
  */
 #ifndef MDTB200_H_
 #define MDTB200_H_
@@ -174,13 +177,44 @@ MDTB200_API int mdtb200_op_gate_res(const float* x, const float* f, const float*
 MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const float* gate, float* df, float* prod, int M, int d,
                                         int rows_per_group, void* stream);
 
+/* PerceiverResampler ---------------------------------------------------------------------------------------
+ * Replaces mdt/models/networks/transformers/perceiver_resampler.py:86-163 (PerceiverResampler.forward), the module that turns the
+ * (B, T, n, d) Voltron token sequence into the num_latents state tokens the denoiser is conditioned on (mdtv_agent.py:392-403).
+ * Weights are bound by the reference state-dict keys ("latents", "time_pos_emb", "layers.{l}.0.norm_media.weight", ...,
+ * "layers.{l}.1.3.weight", "norm.weight"), then committed; forward runs on the stream passed in. */
+typedef struct MdtPerceiverConfig {
+  int32_t abi_version;      /* = MDTB200_ABI_VERSION */
+  int32_t dim;              /* 384 */
+  int32_t depth;            /* 6 (conf/model/mdtv_agent.yaml:28) */
+  int32_t heads;            /* 8 */
+  int32_t dim_head;         /* 64 */
+  int32_t num_latents;      /* 3 = num_tokens_voltron; heads * num_latents <= 64 */
+  int32_t num_time_embeds;  /* 1 */
+  int32_t ff_mult;          /* 4 */
+  int32_t max_batch;
+  int32_t max_features;     /* T * n feature tokens per sample (392) */
+} MdtPerceiverConfig;
+typedef struct MdtPerceiver MdtPerceiver;
+MDTB200_API int         mdtb200_perceiver_create(const MdtPerceiverConfig* cfg, MdtPerceiver** out);
+MDTB200_API void        mdtb200_perceiver_destroy(MdtPerceiver* h);
+MDTB200_API const char* mdtb200_perceiver_last_error(const MdtPerceiver* h);
+MDTB200_API int         mdtb200_perceiver_bind_weight(MdtPerceiver* h, const char* name, const float* dev_ptr, int64_t numel);
+MDTB200_API int         mdtb200_perceiver_commit_weights(MdtPerceiver* h, void* stream);
+/* x_f (B, T, n, dim) device fp32; mask (B, T) device fp32 (1 = frame present) or NULL; out (B, num_latents, dim) */
+MDTB200_API int         mdtb200_perceiver_forward(MdtPerceiver* h, const float* x_f, const float* mask, int B, int T, int n,
+                                                  float* out, void* stream);
+MDTB200_API int64_t     mdtb200_perceiver_launch_count(const MdtPerceiver* h);
+
 /* Fused multi-tensor AdamW + EMA: one launch updates every parameter tensor of an optimizer group (torch.optim.AdamW's update
  * followed by the EMA callback's ema -= (1 - decay) (ema - w), mdt/callbacks/ema.py:117-126).  table: device array of
  * {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; float* ema; int64_t numel; float step_size; float bc2_sqrt}
  * (step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t), t = that parameter's step count); blocks: device array of
- * int32 pairs {tensor index, 4096-element chunk index}, one per CUDA block. */
+ * int32 pairs {tensor index, 4096-element chunk index}, one per CUDA block.
+ * step_dev (optional): device int32 step count; the bias corrections are then computed in the kernel (CUDA-graph capture). */
 MDTB200_API int mdtb200_op_adamw_ema(const void* table, const void* blocks, int n_blocks, float lr, float beta1, float beta2, float eps,
-                                     float weight_decay, float ema_decay, int has_ema, void* stream);
+                                     float weight_decay, float ema_decay, int has_ema, const int* step_dev, void* stream);
+/* device counter mixed into every dropout seed (NULL: off): fresh masks on every replay of a graph-captured training step */
+MDTB200_API int mdtb200_op_set_seed_epoch(const uint64_t* dev_counter);
 
 /* Kernel timeline of everything the library launches (debugging / profiling aid, tools/ktrace.py): capacity > 0 arms the
  * trace, capacity == 0 copies up to max_records {globaltimer ns, tag|event|sm|grid|block} pairs to dst_host and disarms. */

@@ -22,7 +22,9 @@ EXPORTS = [
     "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
     "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time", "mdtb200_debug_ktrace",
     "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
-    "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout", "mdtb200_op_adamw_ema",
+    "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout", "mdtb200_op_adamw_ema", "mdtb200_op_set_seed_epoch",
+    "mdtb200_perceiver_create", "mdtb200_perceiver_destroy", "mdtb200_perceiver_last_error", "mdtb200_perceiver_bind_weight",
+    "mdtb200_perceiver_commit_weights", "mdtb200_perceiver_forward", "mdtb200_perceiver_launch_count",
 ]
 
 
@@ -34,6 +36,11 @@ class MdtConfig(C.Structure):
         ("n_state_tokens", C.c_int32), ("precision", C.c_int32), ("max_batch", C.c_int32),
         ("sigma_data", C.c_float),
     ]
+
+
+class MdtPerceiverConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("abi_version", "dim", "depth", "heads", "dim_head", "num_latents", "num_time_embeds", "ff_mult",
+                                         "max_batch", "max_features")]
 
 
 _lock = threading.Lock()
@@ -88,8 +95,24 @@ def _declare(lib):
     lib.mdtb200_op_dropout.argtypes = [fp, fp, i64, C.c_float, C.c_uint64, vp]
     lib.mdtb200_op_gate_res.argtypes = [fp, fp, fp, fp, i32, i32, i32, vp]
     lib.mdtb200_op_gate_res_bwd.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, vp]
-    lib.mdtb200_op_adamw_ema.argtypes = [vp, vp, i32] + [C.c_float] * 6 + [i32, vp]
+    lib.mdtb200_op_adamw_ema.argtypes = [vp, vp, i32] + [C.c_float] * 6 + [i32, vp, vp]
+    lib.mdtb200_op_set_seed_epoch.argtypes = [vp]
+    lib.mdtb200_op_set_seed_epoch.restype = i32
     lib.mdtb200_op_adamw_ema.restype = i32
+    lib.mdtb200_perceiver_create.argtypes = [C.POINTER(MdtPerceiverConfig), C.POINTER(vp)]
+    lib.mdtb200_perceiver_create.restype = i32
+    lib.mdtb200_perceiver_destroy.argtypes = [vp]
+    lib.mdtb200_perceiver_destroy.restype = None
+    lib.mdtb200_perceiver_last_error.argtypes = [vp]
+    lib.mdtb200_perceiver_last_error.restype = C.c_char_p
+    lib.mdtb200_perceiver_bind_weight.argtypes = [vp, C.c_char_p, fp, i64]
+    lib.mdtb200_perceiver_bind_weight.restype = i32
+    lib.mdtb200_perceiver_commit_weights.argtypes = [vp, vp]
+    lib.mdtb200_perceiver_commit_weights.restype = i32
+    lib.mdtb200_perceiver_forward.argtypes = [vp, fp, fp, i32, i32, i32, fp, vp]
+    lib.mdtb200_perceiver_forward.restype = i32
+    lib.mdtb200_perceiver_launch_count.argtypes = [vp]
+    lib.mdtb200_perceiver_launch_count.restype = i64
     for _n in ("gemm", "group_sum", "colsum", "act", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "gate_res", "gate_res_bwd", "dropout"):
         getattr(lib, "mdtb200_op_" + _n).restype = i32
     return lib

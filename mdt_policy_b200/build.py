@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmdtb200.so")
 SOURCES = [os.path.join(CSRC, "engine.cu")]
-HEADERS = [os.path.join(CSRC, "kernels_simt.cuh"), os.path.join(CSRC, "gemm_tcgen05.cuh"), os.path.join(CSRC, "fused_decoder.cuh"),
+HEADERS = [os.path.join(CSRC, "kernels_simt.cuh"), os.path.join(CSRC, "gemm_tcgen05.cuh"), os.path.join(CSRC, "fused_decoder.cuh"), os.path.join(CSRC, "perceiver.cuh"), os.path.join(CSRC, "perceiver_host.cuh"),
            os.path.join(CSRC, "kernels_train.cuh"), os.path.join(CSRC, "ops_train.cuh"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "mdtb200.h")]
 

@@ -1332,9 +1332,12 @@ MDTB200_API int mdtb200_debug_gemm(MdtHandle* h, const float* A, const float* W,
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16 *a16 = nullptr, *w16 = nullptr, *c16 = nullptr;
   const size_t Mp = (size_t)(M + 127) / 128 * 128;
-  CUDA_TRY(h, cudaMalloc(&a16, Mp * 2 * K * 2));
-  CUDA_TRY(h, cudaMalloc(&w16, (size_t)N * 2 * K * 2));
-  CUDA_TRY(h, cudaMalloc(&c16, Mp * 2 * N * 2));
+  if (cudaMalloc(&a16, Mp * 2 * K * 2) != cudaSuccess || cudaMalloc(&w16, (size_t)N * 2 * K * 2) != cudaSuccess ||
+      cudaMalloc(&c16, Mp * 2 * N * 2) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(a16); cudaFree(w16); cudaFree(c16);            // no scratch is leaked on a failed allocation
+    return fail(h, MDTB200_ENOMEM, "debug_gemm: scratch allocation failed");
+  }
   cudaMemsetAsync(a16, 0, Mp * 2 * K * 2, st);
   split_weights_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, a16, M, K);
   split_weights_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(W, w16, N, K);
@@ -1386,8 +1389,12 @@ MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int e
   cudaStream_t st = (cudaStream_t)stream;
   const size_t Mp = (size_t)(M + 127) / 128 * 128;
   __nv_bfloat16 *a16 = nullptr, *w16 = nullptr, *c16 = nullptr; float *c = nullptr, *gate = nullptr;
-  CUDA_TRY(h, cudaMalloc(&a16, Mp * 2 * K * 2)); CUDA_TRY(h, cudaMalloc(&w16, (size_t)N * 2 * K * 2));
-  CUDA_TRY(h, cudaMalloc(&c16, Mp * 2 * N * 2)); CUDA_TRY(h, cudaMalloc(&c, Mp * N * 4)); CUDA_TRY(h, cudaMalloc(&gate, Mp * N * 4));
+  if (cudaMalloc(&a16, Mp * 2 * K * 2) != cudaSuccess || cudaMalloc(&w16, (size_t)N * 2 * K * 2) != cudaSuccess ||
+      cudaMalloc(&c16, Mp * 2 * N * 2) != cudaSuccess || cudaMalloc(&c, Mp * N * 4) != cudaSuccess || cudaMalloc(&gate, Mp * N * 4) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(a16); cudaFree(w16); cudaFree(c16); cudaFree(c); cudaFree(gate);
+    return fail(h, MDTB200_ENOMEM, "debug_gemm_time: scratch allocation failed");
+  }
   // pseudo-random, non-zero split-bf16 operands (hi ~ U(-1, 1), lo ~ 2^-9 of that), as the graph's GEMMs see them
   fill_operand_kernel<<<(unsigned)((Mp * K + 255) / 256), 256, 0, st>>>(a16, (int64_t)Mp, K, 0x1234u);
   fill_operand_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(w16, (int64_t)N, K, 0x9876u);
@@ -1418,3 +1425,4 @@ MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int e
 }  // extern "C"
 
 #include "ops_train.cuh"
+#include "perceiver_host.cuh"

@@ -338,7 +338,11 @@ struct AttnArgs {
 };
 
 // counter-based uniform in [0,1): splitmix64 of (seed, element index).  Forward and backward regenerate the same mask.
+// g_seed_epoch (optional, mdtb200_op_set_seed_epoch): a device counter mixed into every seed -- the host seeds are frozen when a
+// training step is captured into a CUDA graph, the counter (incremented by a captured op) gives every replay fresh masks.
+__device__ const unsigned long long* g_seed_epoch = nullptr;
 __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
+  if (g_seed_epoch != nullptr) seed += *g_seed_epoch * 0xD1342543DE82EF95ull;
   unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;

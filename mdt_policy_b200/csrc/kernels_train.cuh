@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(AttnBwdArgs a) {
 // parameter tensors of a group in ONE launch: the host passes a table of {param, grad, exp_avg, exp_avg_sq, ema, numel} and a
 // block -> (tensor, chunk) map; every block updates one 4096-element chunk.
 struct AdamTensor { float* p; const float* g; float* m; float* v; float* ema; long long n; float step_size; float bc2_sqrt; };   // 56 bytes
-struct AdamHyper { float lr, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, ema_decay; int has_ema; };   // step_size / bc2_sqrt: per tensor
+struct AdamHyper { float lr, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, ema_decay; int has_ema; const int* step_dev; };   // step_size / bc2_sqrt: per tensor
 constexpr int ADAM_CHUNK = 4096;
 
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float* ema, const AdamHyper& h) {
@@ -379,6 +379,11 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const AdamTensor* __rest
   const int2 bc = blocks[blockIdx.x];
   const AdamTensor t = tab[bc.x];
   h.step_size = t.step_size; h.bc2_sqrt = t.bc2_sqrt;      // torch.optim.AdamW counts steps per parameter
+  if (h.step_dev != nullptr) {                             // capturable mode: the step count lives on the device (CUDA-graph replays)
+    const float tt = (float)*h.step_dev;
+    h.step_size = h.lr / (1.0f - powf(h.beta1, tt));
+    h.bc2_sqrt = sqrtf(1.0f - powf(h.beta2, tt));
+  }
   const long long base = (long long)bc.y * ADAM_CHUNK;
   const long long end = base + ADAM_CHUNK < t.n ? base + ADAM_CHUNK : t.n;
   const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) | reinterpret_cast<uintptr_t>(t.m) |

@@ -255,12 +255,23 @@ MDTB200_API int mdtb200_op_gate_res_bwd(const float* dout, const float* f, const
 // Fused multi-tensor AdamW (+ EMA) step: `table` = device array of AdamTensor records (56 bytes: param, grad, exp_avg, exp_avg_sq,
 // ema pointers, int64 numel, float step_size = lr / (1 - beta1^t), float bc2_sqrt = sqrt(1 - beta2^t) with t the PER-PARAMETER step
 // count, as torch.optim.AdamW keeps it), `blocks` = device array of n_blocks int2 {tensor index, 4096-element chunk index}.
+// step_dev (optional): device int32 step count shared by all tensors of the call -- bias corrections are then computed in the
+// kernel from it (capturable mode: the host-side values would be frozen inside a CUDA graph).
 MDTB200_API int mdtb200_op_adamw_ema(const void* table, const void* blocks, int n_blocks, float lr, float beta1, float beta2, float eps,
-                                     float weight_decay, float ema_decay, int has_ema, void* stream) {
+                                     float weight_decay, float ema_decay, int has_ema, const int* step_dev, void* stream) {
   if (!table || !blocks || n_blocks < 1) return op_fail(MDTB200_EINVAL, "op_adamw_ema: bad argument");
-  AdamHyper h{lr, beta1, beta2, eps, weight_decay, 0.f, 1.f, ema_decay, has_ema};
+  AdamHyper h{lr, beta1, beta2, eps, weight_decay, 0.f, 1.f, ema_decay, has_ema, step_dev};
   adamw_ema_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const AdamTensor*>(table), static_cast<const int2*>(blocks), h);
   return op_check("adamw_ema_kernel");
+}
+
+// Registers a device counter that is mixed into every dropout seed (NULL: off).  Lets a CUDA-graph-captured training step draw
+// fresh dropout masks on every replay: the captured graph increments the counter, the host-side seeds stay frozen.  Process-wide.
+MDTB200_API int mdtb200_op_set_seed_epoch(const uint64_t* dev_counter) {
+  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(dev_counter);
+  cudaError_t e = cudaMemcpyToSymbol(g_seed_epoch, &p, sizeof(p));
+  if (e != cudaSuccess) return op_fail(MDTB200_ECUDA, "op_set_seed_epoch: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 }  // extern "C"

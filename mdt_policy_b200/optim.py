@@ -11,7 +11,9 @@ ONE kernel launch per parameter group: a multi-tensor table {param, grad, exp_av
         ...
 
 ``ema_decay=None`` disables the average; ``ema_schedule=(inv_gamma, power, min, max)`` reproduces ``EMACallback.get_decay``.
-CUDA fp32 parameters only (there is no CPU fallback in this package).
+``capturable=True`` keeps the step count on the device and the pointer table in pinned memory, so ``step()`` can be recorded into a
+CUDA graph (``GraphedTrainStep`` below captures loss forward + backward + this step as ONE graph: the ~1500 launches of a training
+step are issued by the GPU front end instead of by Python).  CUDA fp32 parameters only (there is no CPU fallback in this package).
 """
 from __future__ import annotations
 
@@ -29,13 +31,17 @@ _CHUNK = 4096
 
 class FusedAdamWEMA(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_decay=None, ema_schedule=None,
-                 ema_start_step=0):
+                 ema_start_step=0, capturable=False):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid AdamW hyper-parameter")
         if ema_decay is not None and not (0 <= ema_decay <= 1):
             raise ValueError("EMA decay value must be between 0 and 1")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.ema_decay, self.ema_schedule, self.ema_start_step = ema_decay, ema_schedule, ema_start_step
+        if capturable and (ema_schedule is not None or ema_start_step):
+            raise ValueError("capturable=True supports a constant ema_decay only (host-side schedules are frozen inside a CUDA graph)")
+        self.capturable = capturable
+        self._cap = {}           # group index -> {"step": device int32, "pinned": host table, "table": device table}
         self._lib = _lib.load()
         self._maps = {}          # (group index, tensor sizes with grads) -> device block map
 
@@ -108,7 +114,23 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                 hyper = struct.unpack("q", struct.pack("ff", group["lr"] / (1 - beta1 ** t), math.sqrt(1 - beta2 ** t)))[0]
                 rows.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                              st["ema"].data_ptr() if use_ema else 0, p.numel(), hyper))
-            table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+            step_ptr = None
+            if self.capturable:
+                # device-side step count (incremented by a capturable op) + pinned pointer table copied asynchronously: everything
+                # below is legal inside torch.cuda.graph(); on replay the same table is copied again and the count keeps advancing
+                cap = self._cap.get(gi)
+                if cap is None or cap["pinned"].shape[0] != len(rows):
+                    cap = self._cap[gi] = {"step": torch.zeros(1, dtype=torch.int32, device=dev),
+                                           "pinned": torch.empty(len(rows), 7, dtype=torch.int64).pin_memory(),
+                                           "table": torch.empty(len(rows), 7, dtype=torch.int64, device=dev)}
+                    cap["step"].fill_(max(self.state[p]["step"] for p in params) - 1)
+                cap["pinned"].copy_(torch.tensor(rows, dtype=torch.int64))
+                cap["table"].copy_(cap["pinned"], non_blocking=True)
+                cap["step"].add_(1)
+                cap["grads"] = keep
+                table, step_ptr = cap["table"], C.c_void_p(cap["step"].data_ptr())
+            else:
+                table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
             key = (gi, tuple(p.numel() for p in params))
             blocks = self._maps.get(key)
             if blocks is None or blocks.device != dev:
@@ -118,8 +140,63 @@ class FusedAdamWEMA(torch.optim.Optimizer):
             with torch.cuda.device(dev):
                 rc = self._lib.mdtb200_op_adamw_ema(
                     C.c_void_p(table.data_ptr()), C.c_void_p(blocks.data_ptr()), blocks.shape[0], group["lr"], beta1, beta2, group["eps"],
-                    group["weight_decay"], float(decay), int(use_ema),
+                    group["weight_decay"], float(decay), int(use_ema), step_ptr,
                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             if rc != 0:
                 raise RuntimeError(f"mdtb200_op_adamw_ema failed ({rc}): {self._lib.mdtb200_last_error(None).decode()}")
         return loss
+
+
+class GraphedTrainStep:
+    """One training step -- ``GCDenoiser.loss`` forward, backward and the fused AdamW + EMA update -- captured into a CUDA graph.
+
+        opt = FusedAdamWEMA(model.parameters(), ..., capturable=True)
+        step = GraphedTrainStep(model, opt, state_images, goal, actions, noise, sigma)     # warm-up + capture on example tensors
+        loss = step(state_images, goal, actions, noise, sigma)                             # copy-in, one graph replay
+
+    The eager step issues ~1500 small kernels from Python (two thirds of its wall time is host sequencing); the replayed graph
+    issues them from the GPU front end.  Dropout masks stay fresh on every replay through a device-side RNG epoch counter that the
+    graph increments (``mdtb200_op_set_seed_epoch``); the optimizer's step count lives on the device as well.  Shapes are fixed at
+    capture time (as for any CUDA graph); parameters without a gradient at capture time stay frozen.
+    """
+
+    def __init__(self, model, optimizer: FusedAdamWEMA, state_images, goal, actions, noise, sigma, modality="lang", warmup=3):
+        if not optimizer.capturable:
+            raise ValueError("GraphedTrainStep needs FusedAdamWEMA(capturable=True)")
+        dev = actions.device
+        self.model, self.opt, self.modality = model, optimizer, modality
+        self.static = [t.detach().clone() for t in (state_images, goal, actions, noise, sigma)]
+        lib = _lib.load()
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        if lib.mdtb200_op_set_seed_epoch(C.c_void_p(self.epoch.data_ptr())) != 0:
+            raise RuntimeError("mdtb200_op_set_seed_epoch failed: " + lib.mdtb200_last_error(None).decode())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _body(self):
+        s, g, a, n, sig = self.static
+        self.opt.zero_grad(set_to_none=True)
+        self.epoch.add_(1)
+        loss, _ = self.model.loss({"state_images": s, "modality": self.modality}, a, g, n, sig)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, state_images, goal, actions, noise, sigma):
+        for dst, src in zip(self.static, (state_images, goal, actions, noise, sigma)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def close(self):
+        """unregisters the RNG epoch counter (eager steps go back to host-drawn seeds only)"""
+        _lib.load().mdtb200_op_set_seed_epoch(None)

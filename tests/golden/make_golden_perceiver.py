@@ -29,13 +29,14 @@ def main():
     sys.modules["einops_exts"] = ex
     from mdt.models.networks.transformers.perceiver_resampler import PerceiverResampler
     out = {}
-    for tag, (depth, n_lat, B, nf) in {"shipped": (6, 3, 5, 392), "small": (2, 5, 3, 40)}.items():
+    for tag, (depth, n_lat, B, nf) in {"shipped": (6, 3, 5, 392), "small": (2, 5, 3, 40), "shipped_init": (6, 3, 5, 392)}.items():
         m = PerceiverResampler(dim=384, depth=depth, dim_head=64, heads=8, num_time_embeds=1, num_latents=n_lat).eval()
         named = [(n, tuple(p.shape)) for n, p in m.named_parameters()]
         assert named == H.perceiver_shapes(depth, n_lat), "tests/helpers.perceiver_shapes out of sync with the reference"
-        m.load_state_dict(H.perceiver_state(named, 51))
+        m.load_state_dict(H.perceiver_state(named, 51, "init" if tag.endswith("_init") else "trained"))
         x = synthetic_tensor(f"perceiver.x.{tag}", (B, 1, nf, 384), 52, "init") * 50.0
         out[f"out_{tag}"] = m(x)
+        out[f"out64_{tag}"] = m.double()(x.double()).float()          # the reference in fp64: how much of an error is fp32 noise
         if tag == "small":
             out["names"] = torch.zeros(1)
     save("perceiver", meta=dict(case="perceiver", weight_seed=51, input_seed=52, shipped=[6, 3, 5, 392], small=[2, 5, 3, 40]), **out)

@@ -88,16 +88,18 @@ def perceiver_shapes(depth, n_lat, d=384, inner=512, n_time=1):
     return s + [("norm.weight", (d,)), ("norm.bias", (d,))]
 
 
-def perceiver_state(named_shapes, seed):
-    """synthetic 'trained' PerceiverResampler weights: LayerNorms ~ 1 + N(0, 0.1^2) / N(0, 0.1^2), latents and time embedding
-    ~ N(0, 1) (their reference initialisation), projections ~ N(0, 1/fan_in)."""
+def perceiver_state(named_shapes, seed, profile="trained"):
+    """synthetic PerceiverResampler weights.  latents and time embedding ~ N(0, 1) (their reference initialisation).
+    profile "trained": LayerNorms ~ 1 + N(0, 0.1^2) / N(0, 0.1^2), projections ~ N(0, 1/fan_in) -- O(1) activations everywhere, which
+    drives the softmax of layers >= 2 into saturation (scores sigma ~ 27): a deliberately ill-conditioned stress case.
+    profile "init": LayerNorms 1 / 0, projections ~ N(0, 0.02^2) -- the regime of a freshly initialised model."""
     from mdt_policy_b200.synthetic import synthetic_tensor
     out = {}
     for n, shp in named_shapes:
         if n in ("latents", "time_pos_emb"):
             out[n] = synthetic_tensor(n, shp, seed, "init") * 50.0
         elif "norm" in n or ".1.0." in n:
-            out[n] = synthetic_tensor("p." + n.replace("norm", "ln_norm").replace(".1.0.", ".1.ln_0."), shp, seed, "trained")
+            out[n] = synthetic_tensor("p." + n.replace("norm", "ln_norm").replace(".1.0.", ".1.ln_0."), shp, seed, profile)
         else:
-            out[n] = synthetic_tensor(n, shp, seed, "trained")
+            out[n] = synthetic_tensor(n, shp, seed, profile)
     return out

