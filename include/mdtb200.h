@@ -216,6 +216,33 @@ MDTB200_API int mdtb200_op_adamw_ema(const void* table, const void* blocks, int 
 /* device counter mixed into every dropout seed (NULL: off): fresh masks on every replay of a graph-captured training step */
 MDTB200_API int mdtb200_op_set_seed_epoch(const uint64_t* dev_counter);
 
+/* ---- training primitives, fused (round 2): every tensor is split ONCE into a row-major hi|lo bf16 operand ([rows, 2*cols]) that
+ * serves the forward, input-gradient and weight-gradient GEMMs (the tcgen05 kernel reads it K-major or MN-major), the producers
+ * (LayerNorm, attention, residual backward, activation backward) emit those operands directly, and the small reductions end in
+ * per-CTA partial sums that one mdtb200_op_group_sum finishes.  Same reference ops as above (transformer_blocks.py). */
+MDTB200_API int mdtb200_op_split(const float* x, const float* h, int act, void* out16, float* partial, int M, int K, void* stream);
+MDTB200_API int mdtb200_op_split_rows_per_slab(void);
+MDTB200_API int mdtb200_op_split_multi(const void* table, const void* blocks, int n_blocks, void* stream);
+/* mode 0: C[M,N] = x16[M,2K] . w16[N,2K]^T + bias (epi 6: C = pre-activation, C16[M,2N] = split(GELU(C)));
+ * mode 1: C[M,K] = dy16[M,2N] . w16[N,2K];  mode 2: C[N,K] = dy16[M,2N]^T . x16[M,2K], deterministic split-K over M when
+ * splits > 1 (workspace of mdtb200_op_gemm16_ws floats, zero-initialised self-resetting counters, one per output tile) */
+MDTB200_API int64_t mdtb200_op_gemm16_ws(int N, int K, int splits);
+MDTB200_API int mdtb200_op_gemm16(int mode, const void* A16, const void* B16, const float* bias, float* C, void* C16, int M, int N, int K,
+                                  int epi, int splits, float* sk_ws, unsigned* sk_cnt, void* stream);
+MDTB200_API int mdtb200_op_ln_fwd16(const float* x, const float* w, const float* b, const float* shift, const float* scale, int mod_stride,
+                                    int rows_per_group, int M, int d, float* y, void* y16, void* stream);
+MDTB200_API int mdtb200_op_ln_bwd2(const float* x, const float* dy, const float* w, const float* b, const float* scale, int mod_stride,
+                                   const float* dres, float* dx, float* dshift, float* dscale, int dmod_stride, float* partial, int M, int d,
+                                   int T, void* stream);
+MDTB200_API int mdtb200_op_attn_fwd16(const float* q, int ldq, const float* k, const float* v, int ldkv, void* y16, int B, int H, int hd,
+                                      int Tq, int Tk, int causal, float p_drop, uint64_t seed, void* stream);
+MDTB200_API int mdtb200_op_res_drop_fwd(const float* x, const float* f, const float* gate, int gate_stride, float* out, int M, int d, int T,
+                                        float p, uint64_t seed, void* stream);
+MDTB200_API int mdtb200_op_res_drop_bwd(const float* dout, const float* f, const float* gate, int gate_stride, void* df16, float* dgate,
+                                        int dgate_stride, float* bpartial, int M, int d, int T, float p, uint64_t seed, void* stream);
+MDTB200_API int mdtb200_op_narrow_fwd(const float* x, const float* W, const float* bias, float* y, int M, int K, int J, void* stream);
+MDTB200_API int mdtb200_op_narrow_wgrad(const float* wide, const float* thin, float* partial, int M, int N, int J, int wide_major, void* stream);
+
 /* Kernel timeline of everything the library launches (debugging / profiling aid, tools/ktrace.py): capacity > 0 arms the
  * trace, capacity == 0 copies up to max_records {globaltimer ns, tag|event|sm|grid|block} pairs to dst_host and disarms. */
 MDTB200_API int64_t mdtb200_debug_ktrace(MdtHandle* h, int64_t capacity, unsigned long long* dst_host, int64_t max_records);

@@ -23,6 +23,8 @@ EXPORTS = [
     "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time", "mdtb200_debug_ktrace",
     "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
     "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout", "mdtb200_op_adamw_ema", "mdtb200_op_set_seed_epoch",
+    "mdtb200_op_split", "mdtb200_op_split_rows_per_slab", "mdtb200_op_split_multi", "mdtb200_op_gemm16_ws", "mdtb200_op_gemm16", "mdtb200_op_ln_fwd16",
+    "mdtb200_op_ln_bwd2", "mdtb200_op_attn_fwd16", "mdtb200_op_res_drop_fwd", "mdtb200_op_res_drop_bwd", "mdtb200_op_narrow_fwd", "mdtb200_op_narrow_wgrad",
     "mdtb200_perceiver_create", "mdtb200_perceiver_destroy", "mdtb200_perceiver_last_error", "mdtb200_perceiver_bind_weight",
     "mdtb200_perceiver_commit_weights", "mdtb200_perceiver_forward", "mdtb200_perceiver_launch_count",
 ]
@@ -97,6 +99,23 @@ def _declare(lib):
     lib.mdtb200_op_gate_res_bwd.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, vp]
     lib.mdtb200_op_adamw_ema.argtypes = [vp, vp, i32] + [C.c_float] * 6 + [i32, vp, vp]
     lib.mdtb200_op_set_seed_epoch.argtypes = [vp]
+    f32, u64 = C.c_float, C.c_uint64
+    lib.mdtb200_op_split.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp]
+    lib.mdtb200_op_split_rows_per_slab.argtypes = []
+    lib.mdtb200_op_split_multi.argtypes = [vp, vp, i32, vp]
+    lib.mdtb200_op_gemm16_ws.argtypes = [i32, i32, i32]
+    lib.mdtb200_op_gemm16_ws.restype = C.c_int64
+    lib.mdtb200_op_gemm16.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.mdtb200_op_ln_fwd16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.mdtb200_op_ln_bwd2.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]
+    lib.mdtb200_op_attn_fwd16.argtypes = [vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, u64, vp]
+    lib.mdtb200_op_res_drop_fwd.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]
+    lib.mdtb200_op_res_drop_bwd.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]
+    lib.mdtb200_op_narrow_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.mdtb200_op_narrow_wgrad.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    for fn in ("split", "split_rows_per_slab", "split_multi", "gemm16", "ln_fwd16", "ln_bwd2", "attn_fwd16", "res_drop_fwd", "res_drop_bwd",
+               "narrow_fwd", "narrow_wgrad"):
+        getattr(lib, "mdtb200_op_" + fn).restype = i32
     lib.mdtb200_op_set_seed_epoch.restype = i32
     lib.mdtb200_op_adamw_ema.restype = i32
     lib.mdtb200_perceiver_create.argtypes = [C.POINTER(MdtPerceiverConfig), C.POINTER(vp)]

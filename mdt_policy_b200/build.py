@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmdtb200.so")
 SOURCES = [os.path.join(CSRC, "engine.cu")]
 HEADERS = [os.path.join(CSRC, "kernels_simt.cuh"), os.path.join(CSRC, "gemm_tcgen05.cuh"), os.path.join(CSRC, "fused_decoder.cuh"), os.path.join(CSRC, "perceiver.cuh"), os.path.join(CSRC, "perceiver_host.cuh"),
            os.path.join(CSRC, "kernels_train.cuh"), os.path.join(CSRC, "ops_train.cuh"),
+           os.path.join(CSRC, "kernels_train2.cuh"), os.path.join(CSRC, "ops_train2.cuh"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "mdtb200.h")]
 
 NVCC_FLAGS = [

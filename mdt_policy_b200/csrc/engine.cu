@@ -1424,5 +1424,5 @@ MDTB200_API int mdtb200_debug_gemm_time(MdtHandle* h, int M, int N, int K, int e
 
 }  // extern "C"
 
-#include "ops_train.cuh"
+#include "ops_train2.cuh"
 #include "perceiver_host.cuh"

@@ -37,6 +37,14 @@ struct TcGemm {
   int gi, go, goff;            // output-row remap (row = (m / gi) * go + goff + m % gi; gi == 0: identity), C / C16 only
   int wg_rows, wg_stride, w_rows;   // weight groups: rows [g * wg_rows, +wg_rows) of A use W rows [g * wg_stride + n, ...) (w_rows = total W rows)
   int w_dynamic;                    // 1: W is written by the preceding kernel on the stream (training ops): no W prefetch ahead of the PDL wait
+  // MN-major operands (training: one row-major hi|lo split per tensor serves forward, dgrad and wgrad -- no transposed copies):
+  //   a_mn: A16 is [K (reduce) rows, lda16] with element (m, k) at A16[k * lda16 + m], lo half at column lda16 / 2 + m
+  //   w_mn: W16 is [K (reduce) rows, ldw16] with element (n, k) at W16[k * ldw16 + n], lo half at column ldw16 / 2 + n
+  // K need not be a multiple of 64 when both operands are MN-major (TMA zero-fills the rows past K).
+  int a_mn, w_mn, ldw16;
+  // split-K (deterministic): grid.z = splits CTAs per tile write fp32 partial tiles to sk_ws, the last one to arrive (sk_cnt, self-
+  // resetting counters, one per tile, zeroed once by the owner) adds them in slice order and runs the epilogue.
+  int splits; float* sk_ws; unsigned* sk_cnt;
 };
 
 struct TcParams {
@@ -48,6 +56,8 @@ struct TcParams {
   int gi, go, goff;
   int wg_rows, wg_stride;
   int w_early;                 // 1: W is static (inference weights): its first tiles may be requested before the dependency wait
+  int a_mn, w_mn, a_lo, w_lo;  // MN-major operand flags and the column offset of their lo halves
+  int splits; float* sk_ws; unsigned* sk_cnt;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -149,7 +159,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// cute::UMMA::InstrDescriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at bit 17, M>>4 at bit 24
+// MN-major SWIZZLE_128B descriptor (cute mma_traits_sm100.hpp, make_umma_desc<Major::MN>: canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO))
+// in 16-byte units): the tile is stored as TMA boxes of 64 reduce-rows x 64 MN-elements (128-byte rows): 8 k-rows = 1024 B (SBO),
+// the next 64 MN-elements are the next 8 KB box (LBO); one UMMA_K = 16 step advances the start address by 16 rows = 2048 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), K-major both (bit 15 / 16 = 1: A / B MN-major),
+// N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -187,8 +210,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int n0w = n0 + (p.wg_rows ? (m0 / p.wg_rows) * p.wg_stride : 0);     // W row of this tile (weight groups, e.g. one per head)
-  const int nkb = p.K / BK;
+  const int nkb_all = (p.K + BK - 1) / BK;
+  const int kb_beg = p.splits > 1 ? (int)((long)nkb_all * blockIdx.z / p.splits) : 0;
+  const int kb_end = p.splits > 1 ? (int)((long)nkb_all * (blockIdx.z + 1) / p.splits) : nkb_all;
+  const int nkb = kb_end - kb_beg;           // k-blocks of this CTA (split-K: a slice of the reduce dimension)
   if (threadIdx.x == 0) TC_STAMP(0);
+  // operand tile loads: K-major = one box {64 k, rows}; MN-major = boxes {64 mn, 64 k} (8 KB each) along the MN extent
+  auto load_a = [&](uint32_t dst, uint32_t bar, int kb, int lo) {
+    if (!p.a_mn) tma_load_2d(dst, &tmA, bar, (lo ? p.K : 0) + kb * BK, m0);
+    else {
+#pragma unroll
+      for (int j = 0; j < BM / 64; ++j) tma_load_2d(dst + j * 8192, &tmA, bar, (lo ? p.a_lo : 0) + m0 + 64 * j, kb * BK);
+    }
+  };
+  auto load_w = [&](uint32_t dst, uint32_t bar, int kb, int lo) {
+    if (!p.w_mn) tma_load_2d(dst, &tmW, bar, (lo ? p.K : 0) + kb * BK, n0w);
+    else {
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * 8192, &tmW, bar, (lo ? p.w_lo : 0) + n0w + 64 * j, kb * BK);
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -211,8 +252,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int kb = 0; kb < npre; ++kb) {
       const uint32_t st = sbase + kb * L::STAGE;
       mbar_expect_tx(full_bar(kb), L::STAGE);
-      tma_load_2d(st + L::A_TILE, &tmW, full_bar(kb), kb * BK, n0w);                                         // W hi
-      if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(kb), p.K + kb * BK, n0w);  // W lo
+      load_w(st + L::A_TILE, full_bar(kb), kb_beg + kb, 0);                                         // W hi
+      if (PASSES == 3) load_w(st + 2 * L::A_TILE + L::W_TILE, full_bar(kb), kb_beg + kb, 1);        // W lo
     }
   }
   pdl_wait(KT_GEMM);       // prologue above overlapped the previous kernel's tail; its results are visible from here on
@@ -228,17 +269,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kb >= npre) {
           mbar_wait(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), L::STAGE);
-          tma_load_2d(st + L::A_TILE, &tmW, full_bar(s), kb * BK, n0w);                                         // W hi
-          if (PASSES == 3) tma_load_2d(st + 2 * L::A_TILE + L::W_TILE, &tmW, full_bar(s), p.K + kb * BK, n0w);  // W lo
+          load_w(st + L::A_TILE, full_bar(s), kb_beg + kb, 0);                                         // W hi
+          if (PASSES == 3) load_w(st + 2 * L::A_TILE + L::W_TILE, full_bar(s), kb_beg + kb, 1);        // W lo
         }
-        tma_load_2d(st, &tmA, full_bar(s), kb * BK, m0);                                                       // A hi
-        if (PASSES == 3) tma_load_2d(st + L::A_TILE + L::W_TILE, &tmA, full_bar(s), p.K + kb * BK, m0);        // A lo
+        load_a(st, full_bar(s), kb_beg + kb, 0);                                                       // A hi
+        if (PASSES == 3) load_a(st + L::A_TILE + L::W_TILE, full_bar(s), kb_beg + kb, 1);              // A lo
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, BN) | (p.a_mn ? 1u << 15 : 0u) | (p.w_mn ? 1u << 16 : 0u);
+      const uint32_t a_step = p.a_mn ? 2048 >> 4 : (UMMA_K * 2) >> 4, w_step = p.w_mn ? 2048 >> 4 : (UMMA_K * 2) >> 4;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % L::STAGES;
         const uint32_t ph = (kb / L::STAGES) & 1;
@@ -247,17 +289,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kb == 0) TC_STAMP(2);
         if (kb == nkb - 1) TC_STAMP(3);
         const uint32_t st = sbase + s * L::STAGE;
-        const uint64_t a_hi = make_smem_desc(st), w_hi = make_smem_desc(st + L::A_TILE);
-        const uint64_t a_lo = make_smem_desc(st + L::A_TILE + L::W_TILE), w_lo = make_smem_desc(st + 2 * L::A_TILE + L::W_TILE);
+        const uint64_t a_hi = p.a_mn ? make_smem_desc_mn(st) : make_smem_desc(st);
+        const uint64_t w_hi = p.w_mn ? make_smem_desc_mn(st + L::A_TILE) : make_smem_desc(st + L::A_TILE);
+        const uint64_t a_lo = p.a_mn ? make_smem_desc_mn(st + L::A_TILE + L::W_TILE) : make_smem_desc(st + L::A_TILE + L::W_TILE);
+        const uint64_t w_lo = p.w_mn ? make_smem_desc_mn(st + 2 * L::A_TILE + L::W_TILE) : make_smem_desc(st + 2 * L::A_TILE + L::W_TILE);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);     // +32 bytes per UMMA_K inside the 128-byte swizzle row
+          // K-major: +32 bytes per UMMA_K inside the 128-byte swizzle row; MN-major: +16 rows of 128 bytes
+          const uint64_t ada = (uint64_t)(k * a_step), adw = (uint64_t)(k * w_step);
           if (PASSES == 3) {
-            umma_f16(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);   // small terms first
-            umma_f16(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
-            umma_f16(tmem_base, a_hi + adv, w_hi + adv, idesc, 1);
+            umma_f16(tmem_base, a_lo + ada, w_hi + adw, idesc, (kb | k) != 0);   // small terms first
+            umma_f16(tmem_base, a_hi + ada, w_lo + adw, idesc, 1);
+            umma_f16(tmem_base, a_hi + ada, w_hi + adw, idesc, 1);
           } else {
-            umma_f16(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            umma_f16(tmem_base, a_hi + ada, w_hi + adw, idesc, (kb | k) != 0);
           }
         }
         umma_commit(empty_bar(s));          // smem slot reusable once these MMAs have read it
@@ -309,14 +354,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+        if (nkb == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = 0.f;        // empty split-K slice: nothing was accumulated
+        }
+        if (p.bias && p.splits <= 1) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + col + j);
             o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
           }
         }
-        if (p.epi == EPI_GELU) {
+        if (p.epi == EPI_GELU && p.splits <= 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = gelu_erf_fast(o[j]);
         }
@@ -328,13 +377,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 64) TC_STAMP(5);     // a warp-2 thread: phase A done (did not run the producer / MMA loops)
     __syncthreads();
     if (threadIdx.x == 64) TC_STAMP(6);
+    bool finish = true;
+    if (p.splits > 1) {
+      // split-K: publish this slice's raw tile, count arrivals; the last CTA of the tile sums the slices in slice order
+      // (deterministic), applies bias / activation and continues into phase B; the others are done.
+      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      float* ws = p.sk_ws + (size_t)tile * p.splits * (BM * BN);
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int idx = threadIdx.x + it * NT;
+        const int r = idx / GPR, cg = (idx % GPR) * 8;
+        float* dst = ws + (size_t)blockIdx.z * (BM * BN) + r * BN + cg;
+        __stcg(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(stage + r * SP + cg));
+        __stcg(reinterpret_cast<float4*>(dst + 4), *reinterpret_cast<const float4*>(stage + r * SP + cg + 4));
+      }
+      __threadfence();
+      __syncthreads();
+      volatile int* s_last = reinterpret_cast<volatile int*>(smem + L::BAR_OFF + 8 * (2 * L::STAGES + 1) + 8);
+      if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(p.sk_cnt + tile, 1u);
+        const int last = old == (unsigned)(p.splits - 1);
+        if (last) p.sk_cnt[tile] = 0u;              // self-reset: the next launch finds the counters zero again
+        *s_last = last;
+      }
+      __syncthreads();
+      finish = *s_last != 0;
+      if (finish) {
+        __threadfence();
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+          const int idx = threadIdx.x + it * NT;
+          const int r = idx / GPR, cg = (idx % GPR) * 8;
+          float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+          for (int z = 0; z < p.splits; ++z) {
+            const float* src = ws + (size_t)z * (BM * BN) + r * BN + cg;
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(src)), b = __ldcg(reinterpret_cast<const float4*>(src + 4));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+          }
+          float o[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += p.bias[n0 + cg + j];
+          }
+          if (p.epi == EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = gelu_erf_fast(o[j]);
+          }
+          *reinterpret_cast<float4*>(stage + r * SP + cg) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(stage + r * SP + cg + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
     // phase B (coalesced): consecutive threads own consecutive 8-column groups of a row -> full-line global loads/stores
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
       const int idx = threadIdx.x + it * NT;
       const int r = idx / GPR, cg = (idx % GPR) * 8;
       const int row = m0 + r;
-      if (row >= p.M) continue;
+      if (row >= p.M || !finish) continue;
       const int nb = n0 + cg;
       float o[8];
       {
@@ -367,6 +467,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* cr = p.C + (size_t)orow * p.ldc + nb;
         *reinterpret_cast<float4*>(cr) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4*>(cr + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (p.epi == EPI_GELU16) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = gelu_erf_fast(o[t]);
       }
       if (p.C16) {
         __align__(16) __nv_bfloat16 hi[8];
@@ -455,14 +559,17 @@ inline const char* configure_kernels() {
 
 template <int BN, int PASSES>
 inline void launch_one(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
-  dim3 grid(p.N / BN, (p.M + BM - 1) / BM);
+  dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.splits > 1 ? p.splits : 1);
   launch_pdl(tc_gemm_kernel<BN, PASSES>, grid, dim3(THREADS), SmemLayout<BN, PASSES>::TOTAL, st, a, w, p);
 }
 
 // returns nullptr on success, an error message otherwise
 inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t st) {
-  if (g.K % BK != 0 || g.N % 64 != 0 || g.M < 1) return "unsupported GEMM shape (need K % 64 == 0, N % 64 == 0)";
-  if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE) return "unsupported epilogue";
+  if (g.N % 64 != 0 || g.M < 1 || g.K < 1) return "unsupported GEMM shape (need N % 64 == 0)";
+  if ((!g.a_mn || !g.w_mn) && g.K % BK != 0) return "unsupported GEMM shape (a K-major operand needs K % 64 == 0)";
+  if ((g.a_mn || g.w_mn) && (g.wg_rows || g.passes != 3)) return "MN-major operands: no weight groups, bf16x3 only";
+  if (g.splits > 1 && (!g.sk_ws || !g.sk_cnt || g.splits > (g.K + BK - 1) / BK || g.C16 || g.gi)) return "bad split-K configuration";
+  if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE && g.epi != EPI_GELU16) return "unsupported epilogue";
   // tile-N choice (measured, profiles/r01_experiments.md): 128 columns for the wide GEMMs (N >= 1024), 64 for N = d; the
   // 192-column tile turns the fused QKV (N = 1152) into a single wave when a full batch is launched at once (mt >= 16).
   // A "widest tile that still fills ~1 wave, else narrowest" policy was 11 % slower end to end and no better for training.
@@ -477,10 +584,15 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   }
   CUtensorMap ta, tw;
   const char* e;
-  if ((e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta))) return e;
-  if ((e = enc.get(g.W16, g.w_rows > 0 ? g.w_rows : g.N, 2 * g.K, 2 * g.K, bn, &tw))) return e;
+  if (g.a_mn) e = enc.get(g.A16, g.K, g.lda16, g.lda16, BK, &ta);
+  else e = enc.get(g.A16, g.M, 2 * g.K, g.lda16, BM, &ta);
+  if (e) return e;
+  if (g.w_mn) e = enc.get(g.W16, g.K, g.ldw16, g.ldw16, BK, &tw);
+  else e = enc.get(g.W16, g.w_rows > 0 ? g.w_rows : g.N, 2 * g.K, g.ldw16 > 0 ? g.ldw16 : 2 * g.K, bn, &tw);
+  if (e) return e;
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
-             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride, g.w_dynamic ? 0 : 1};
+             g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride, g.w_dynamic ? 0 : 1,
+             g.a_mn, g.w_mn, g.lda16 / 2, g.ldw16 / 2, g.splits > 1 ? g.splits : 1, g.sk_ws, g.sk_cnt};
   if (g.passes == 3) {
     if (bn == 192) launch_one<192, 3>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {

@@ -98,7 +98,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // ------------------------------------------------------------------------------------------
 // Exact fp32 GEMM:  C[M,N] = epi( A[M,K] . W[N,K]^T + bias[N] )
 // 128x64x16 tiles, 256 threads, 8x4 micro-tile per thread, register-prefetched double buffering.
-enum Epi : int { EPI_NONE = 0, EPI_GELU = 1, EPI_MISH = 2, EPI_SILU = 3, EPI_RES = 4, EPI_RES_GATE = 5 };
+enum Epi : int { EPI_NONE = 0, EPI_GELU = 1, EPI_MISH = 2, EPI_SILU = 3, EPI_RES = 4, EPI_RES_GATE = 5,
+                 EPI_GELU16 = 6 };   // tcgen05 GEMM only (training): fp32 output = pre-activation, split-bf16 output = GELU of it
 
 struct GemmArgs {
   const float* A; int lda;

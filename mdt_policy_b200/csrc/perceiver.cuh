@@ -149,113 +149,157 @@ __global__ void __launch_bounds__(256) perceiver_qpath_kernel(QPathArgs a) {
   }
 }
 
-// asynchronous 16-byte global -> shared copies (LDGSTS): every copy of a tile is in flight at once, no register staging
+// ---- warp-level tensor-core helpers for the two passes over xhat (3xTF32: fp32 operands split into tf32 hi + lo, three
+// mma.sync.m16n8k8 per product with fp32 accumulation -> ~2^-21 relative operand error, i.e. fp32-grade scores) ----
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
+}
+// D += A(16x8, row) . B(8x8, col); fragment layout (g = lane / 4, t = lane % 4): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// b0 (k = t, n = g) b1 (k = t+4, n = g); d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(d, al, bh0, bh1);      // small terms first
+  mma_tf32(d, ah, bl0, bl1);
+  mma_tf32(d, ah, bh0, bh1);
+}
 
-// scores[b, r, f] = qtilde[r] . xhat[b, f] + cq[r]      r = h*Q + q < HQ <= 64; CTA = (SC_CH features of one sample): the HQ feature-space
-// queries are loaded once, the features stream through two 32-row tiles filled by cp.async while the previous tile is consumed.
+// scores[b, r, f] = qtilde[r] . xhat[b, f] + cq[r]      r = h*Q + q < HQ <= 8 NT.   CTA = 64 features of one sample, warp = 16 of
+// them (one m-tile); the feature-space queries sit in shared memory as tf32 hi / lo planes, the features stream from global memory
+// straight into the A fragments (each xhat element is used by exactly one warp) as 16-byte loads: within a 16-column chunk lane t
+// owns columns 4t..4t+3, which are the k indices (t, t+4) of two consecutive k-steps -- the same permutation is applied to B.
 struct ScoreArgs { const float* qt; const float* cq; const float* xhat; float* scores; int B, F, Fp, Q, H, Mp, d; };
-constexpr int SC_FT = 32, SC_CH = 128;
-inline size_t score_smem_bytes(int HQ, int d) { return (size_t)(HQ + 2 * SC_FT) * (d + 4) * sizeof(float); }
-__global__ void __launch_bounds__(256) perceiver_scores_kernel(ScoreArgs a) {
+constexpr int SC_FPC = 64, SC_THREADS = 128;
+inline int attn_nt(int HQ) { const int n = (HQ + 7) / 8; return n <= 4 ? n : n <= 6 ? 6 : 8; }     // instantiated n-tile counts: 1 2 3 4 6 8
+inline int score_dp(int d) { return d + 16; }                         // row stride = 16 (mod 32) words: conflict-free LDS.128 fragments
+inline size_t score_smem_bytes(int HQ, int d) { return (size_t)2 * attn_nt(HQ) * 8 * score_dp(d) * sizeof(float); }
+template <int NT>
+__global__ void __launch_bounds__(SC_THREADS) perceiver_scores_kernel(ScoreArgs a) {
   extern __shared__ __align__(16) float sc_smem[];
   pdl_enter();
-  const int d = a.d, DP = d + 4, D4 = d / 4, HQ = a.H * a.Q;
-  float* sq = sc_smem;                 // [HQ][DP]
-  float* sx = sq + HQ * DP;            // [2][SC_FT][DP]
-  const int b = blockIdx.y, fbeg = blockIdx.x * SC_CH, tid = threadIdx.x;
-  const int fend = fbeg + SC_CH < a.F ? fbeg + SC_CH : a.F;
-  auto load_tile = [&](int buf, int f0) {
-    float* dst = sx + buf * SC_FT * DP;
-    for (int e = tid; e < SC_FT * D4; e += 256) {
-      const int fl = e / D4, c = (e % D4) * 4;
-      if (f0 + fl < a.F) cp_async16(dst + fl * DP + c, a.xhat + ((size_t)b * a.F + f0 + fl) * d + c);
-      else *reinterpret_cast<float4*>(dst + fl * DP + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int d = a.d, DP = d + 16, D4 = d / 4, HQ = a.H * a.Q, NR = NT * 8;
+  uint32_t* qh = reinterpret_cast<uint32_t*>(sc_smem);      // [NR][DP] tf32 hi
+  uint32_t* ql = qh + NR * DP;                             // [NR][DP] tf32 lo
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int e0 = 0; e0 < NR * D4; e0 += SC_THREADS * 6) {         // batches of 6 independent 16-byte loads per thread
+    float4 v[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int e = e0 + u * SC_THREADS + tid, r = e / D4, c = (e % D4) * 4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < NR * D4 && r < HQ) v[u] = *reinterpret_cast<const float4*>(a.qt + ((size_t)(r / a.Q) * a.Mp + (size_t)b * a.Q + r % a.Q) * d + c);
     }
-  };
-  for (int e = tid; e < HQ * D4; e += 256) {
-    const int r = e / D4, c = (e % D4) * 4, h = r / a.Q, qi = r % a.Q;
-    cp_async16(sq + r * DP + c, a.qt + ((size_t)h * a.Mp + (size_t)b * a.Q + qi) * d + c);
-  }
-  load_tile(0, fbeg);
-  cp_async_commit();
-  const int fl = tid & 31, rg = tid >> 5;          // lanes = features (conflict-free rows), warp = row group (broadcast q rows)
-  int buf = 0;
-  for (int f0 = fbeg; f0 < fend; f0 += SC_FT, buf ^= 1) {
-    if (f0 + SC_FT < fend) load_tile(buf ^ 1, f0 + SC_FT);
-    cp_async_commit();
-    cp_async_wait<1>();                 // the tile requested one iteration ago (and the queries) have landed
-    __syncthreads();
-    float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const float* xp = sx + buf * SC_FT * DP + fl * DP;
-    for (int c = 0; c < d; c += 4) {
-      const float4 xv = *reinterpret_cast<const float4*>(xp + c);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = rg + 8 * k;
-        if (r < HQ) {
-          const float4 qv = *reinterpret_cast<const float4*>(sq + r * DP + c);
-          acc[k] = fmaf(xv.x, qv.x, acc[k]); acc[k] = fmaf(xv.y, qv.y, acc[k]); acc[k] = fmaf(xv.z, qv.z, acc[k]); acc[k] = fmaf(xv.w, qv.w, acc[k]);
-        }
+    for (int u = 0; u < 6; ++u) {
+      const int e = e0 + u * SC_THREADS + tid, r = e / D4, c = (e % D4) * 4;
+      if (e < NR * D4) {
+        uint4 hi, lo;
+        tf32_split(v[u].x, hi.x, lo.x); tf32_split(v[u].y, hi.y, lo.y); tf32_split(v[u].z, hi.z, lo.z); tf32_split(v[u].w, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(qh + r * DP + c) = hi;
+        *reinterpret_cast<uint4*>(ql + r * DP + c) = lo;
       }
     }
-    if (f0 + fl < a.F) {
+  }
+  __syncthreads();
+  const int f_a = blockIdx.x * SC_FPC + warp * 16 + g, f_b = f_a + 8;
+  if (blockIdx.x * SC_FPC + warp * 16 >= a.F) return;
+  const float* xa = a.xhat + ((size_t)b * a.F + (f_a < a.F ? f_a : a.F - 1)) * d + 4 * t;
+  const float* xb = a.xhat + ((size_t)b * a.F + (f_b < a.F ? f_b : a.F - 1)) * d + 4 * t;
+  float acc[NT][4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = rg + 8 * k;
-        if (r < HQ) a.scores[((size_t)b * HQ + r) * a.Fp + f0 + fl] = acc[k] + a.cq[((size_t)b * a.Q + r % a.Q) * a.H + r / a.Q];
+  for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  const uint32_t* bh = qh + g * DP + 4 * t;
+  const uint32_t* bl = ql + g * DP + 4 * t;
+  // register ring of SC_PF chunks: the loads of chunk j + SC_PF are issued as soon as chunk j has been consumed, so SC_PF
+  // 16-byte loads per row stay in flight per thread (the loop is otherwise bound by one global-memory latency per chunk)
+  constexpr int SC_PF = 6;
+  const int nj = d / 16;
+  float4 ra[SC_PF], rb[SC_PF];
+#pragma unroll
+  for (int u = 0; u < SC_PF; ++u) {
+    ra[u] = u < nj ? __ldg(reinterpret_cast<const float4*>(xa + 16 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb[u] = u < nj ? __ldg(reinterpret_cast<const float4*>(xb + 16 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int j0 = 0; j0 < nj; j0 += SC_PF) {
+#pragma unroll
+    for (int u = 0; u < SC_PF; ++u) {
+      const int j = j0 + u;
+      if (j >= nj) break;
+      const float4 va = ra[u], vb = rb[u];
+      if (j + SC_PF < nj) {
+        ra[u] = __ldg(reinterpret_cast<const float4*>(xa + 16 * (j + SC_PF)));
+        rb[u] = __ldg(reinterpret_cast<const float4*>(xb + 16 * (j + SC_PF)));
+      }
+      uint32_t ah0[4], al0[4], ah1[4], al1[4];
+      tf32_split(va.x, ah0[0], al0[0]); tf32_split(vb.x, ah0[1], al0[1]); tf32_split(va.y, ah0[2], al0[2]); tf32_split(vb.y, ah0[3], al0[3]);
+      tf32_split(va.z, ah1[0], al1[0]); tf32_split(vb.z, ah1[1], al1[1]); tf32_split(va.w, ah1[2], al1[2]); tf32_split(vb.w, ah1[3], al1[3]);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const uint4 h4 = *reinterpret_cast<const uint4*>(bh + n * 8 * DP + 16 * j);
+        const uint4 l4 = *reinterpret_cast<const uint4*>(bl + n * 8 * DP + 16 * j);
+        mma_3x(acc[n], ah0, al0, h4.x, h4.y, l4.x, l4.y);
+        mma_3x(acc[n], ah1, al1, h4.z, h4.w, l4.z, l4.w);
       }
     }
-    __syncthreads();                    // everyone is done with `buf` before the next iteration refills it
   }
-  cp_async_wait<0>();
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = n * 8 + 2 * t + (i & 1), f = (i & 2) ? f_b : f_a;
+      if (r < HQ && f < a.F) a.scores[((size_t)b * HQ + r) * a.Fp + f] = acc[n][i] + a.cq[((size_t)b * a.Q + r % a.Q) * a.H + r / a.Q];
+    }
+  }
 }
 
 // softmax over the F feature keys + Q latent keys (perceiver_resampler.py:69-79), then
 //   z[r, cols] = sum_f alpha[r, f] xhat[f, cols]  -> split-bf16 operand (head-major rows), wsum[row, h] = sum_f alpha[r, f],
-//   olat[row, h*64 + c] = sum_j alpha[r, F + j] v_lat[j, h*64 + c]                      CTA = (96-column tile, sample)
+//   olat[row, h*64 + c] = sum_j alpha[r, F + j] v_lat[j, h*64 + c]
+// CTA = (128-column tile, sample), warp = 32 columns = two m-tiles of z^T[c, r] = sum_f xhat[f, c] alpha[r, f]: lane (g, t) loads
+// xhat[k0 + t (+4)][c_w + 4g .. +3] (full 128-byte lines per warp); its four columns are rows (g, g+8) of the two m-tiles.
 struct ZArgs {
   const float* scores; const float* qkv; int ldq; int inner; const float* xhat;
   __nv_bfloat16* z16; float* wsum; float* olat; int B, F, Fp, Q, H, Mp, d;
 };
-constexpr int Z_CT = 96, Z_FT = 56;       // 392 = 7 x 56 feature rows per tile
-inline size_t z_smem_bytes(int HQ, int F, int Q) { return ((size_t)HQ * (F + Q + 1) + (size_t)2 * Z_FT * (Z_CT + 4)) * sizeof(float); }
-__global__ void __launch_bounds__(256) perceiver_softmax_z_kernel(ZArgs a) {
+constexpr int Z_CT = 128, Z_THREADS = 128;
+inline int z_sp(int F, int Q) { return (F + Q + 3) / 8 * 8 + 4; }     // row stride = 4 (mod 8) words >= F + Q: conflict-free LDS.32 B fragments
+inline size_t z_smem_bytes(int HQ, int F, int Q) { return (size_t)2 * attn_nt(HQ) * 8 * z_sp(F, Q) * sizeof(float); }
+template <int NT>
+__global__ void __launch_bounds__(Z_THREADS) perceiver_softmax_z_kernel(ZArgs a) {
   extern __shared__ __align__(16) float z_smem[];
   pdl_enter();
-  const int HQ = a.H * a.Q, NK = a.F + a.Q, SP = NK + 1, d = a.d;
-  float* sa = z_smem;                       // [HQ][SP] scores -> probabilities
-  float* sx = sa + (size_t)((HQ * SP + 3) / 4) * 4;     // [2][Z_FT][Z_CT + 4], 16-byte aligned
-  const int b = blockIdx.y, c0 = blockIdx.x * Z_CT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  auto load_tile = [&](int buf, int f0) {
-    float* dst = sx + buf * Z_FT * (Z_CT + 4);
-    for (int e = tid; e < Z_FT * (Z_CT / 4); e += 256) {
-      const int fl = e / (Z_CT / 4), cc = (e % (Z_CT / 4)) * 4;
-      if (f0 + fl < a.F) cp_async16(dst + fl * (Z_CT + 4) + cc, a.xhat + ((size_t)b * a.F + f0 + fl) * d + c0 + cc);
-      else *reinterpret_cast<float4*>(dst + fl * (Z_CT + 4) + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  load_tile(0, 0);                          // the first feature tile streams in while the softmax is computed
-  cp_async_commit();
-  for (int e = tid; e < HQ * a.F; e += 256) sa[(e / a.F) * SP + e % a.F] = a.scores[((size_t)b * HQ + e / a.F) * a.Fp + e % a.F];
-  for (int e = tid; e < HQ * a.Q; e += 256) {          // latent keys: q_hq . k_lat[j, h]  (the scale is already inside q)
+  const int HQ = a.H * a.Q, NK = a.F + a.Q, SP = (NK + 3) / 8 * 8 + 4, d = a.d, NR = NT * 8;
+  float* sa = z_smem;                                        // [NR][SP] scores -> probabilities -> tf32 hi
+  uint32_t* sl = reinterpret_cast<uint32_t*>(sa + NR * SP);  // [NR][SP] tf32 lo
+  const int b = blockIdx.y, c0 = blockIdx.x * Z_CT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int F4 = a.F / 4;
+  for (int e = tid; e < HQ * F4; e += Z_THREADS) cp_async16(sa + (e / F4) * SP + (e % F4) * 4, a.scores + ((size_t)b * HQ + e / F4) * a.Fp + (e % F4) * 4);
+  for (int e = tid; e < HQ * (a.F - F4 * 4); e += Z_THREADS) {
+    const int r = e / (a.F - F4 * 4), f = F4 * 4 + e % (a.F - F4 * 4);
+    sa[r * SP + f] = a.scores[((size_t)b * HQ + r) * a.Fp + f];
+  }
+  for (int e = tid; e < HQ * a.Q; e += Z_THREADS) {          // latent keys: q_hq . k_lat[j, h]  (the scale is already inside q)
     const int r = e / a.Q, j = e % a.Q, h = r / a.Q, qi = r % a.Q;
-    const float* qp = a.qkv + ((size_t)b * a.Q + qi) * a.ldq + h * 64;
-    const float* kp = a.qkv + ((size_t)b * a.Q + j) * a.ldq + a.inner + h * 64;
+    const float4* qp = reinterpret_cast<const float4*>(a.qkv + ((size_t)b * a.Q + qi) * a.ldq + h * 64);
+    const float4* kp = reinterpret_cast<const float4*>(a.qkv + ((size_t)b * a.Q + j) * a.ldq + a.inner + h * 64);
     float acc = 0.f;
-    for (int c = 0; c < 64; ++c) acc = fmaf(qp[c], kp[c], acc);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { const float4 x = qp[c], y = kp[c]; acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc); }
     sa[r * SP + a.F + j] = acc;
   }
+  cp_async_wait_all();
   __syncthreads();
-  for (int r = warp; r < HQ; r += 8) {                 // warp per row: max, exp, sum
+  for (int r = warp; r < NR; r += Z_THREADS / 32) {          // warp per row: max, exp, sum; then the tf32 planes (zero padding rows / keys)
     float* row = sa + r * SP;
+    uint32_t* rlo = sl + r * SP;
+    if (r >= HQ) { for (int k = lane; k < SP; k += 32) { row[k] = 0.f; rlo[k] = 0u; } continue; }
     float mx = -INFINITY;
     for (int k = lane; k < NK; k += 32) mx = fmaxf(mx, row[k]);
     mx = warp_max(mx);
@@ -264,63 +308,115 @@ __global__ void __launch_bounds__(256) perceiver_softmax_z_kernel(ZArgs a) {
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     float ws = 0.f;
-    for (int k = lane; k < NK; k += 32) { const float p = row[k] * inv; row[k] = p; if (k < a.F) ws += p; }
+    for (int k = lane; k < SP; k += 32) {
+      const float p = k < NK ? row[k] * inv : 0.f;
+      if (k < a.F) {
+        ws += p;
+        uint32_t hi, lo;
+        tf32_split(p, hi, lo);
+        row[k] = __uint_as_float(hi); rlo[k] = lo;
+      } else {
+        row[k] = p; rlo[k] = 0u;           // latent-key probabilities stay fp32 (used by the olat sum below, never by the MMAs)
+      }
+    }
     ws = warp_sum(ws);
     if (lane == 0 && blockIdx.x == 0) a.wsum[((size_t)b * a.Q + r % a.Q) * a.H + r / a.Q] = ws;
   }
   __syncthreads();
   if (blockIdx.x == 0) {
-    for (int e = tid; e < HQ * 64; e += 256) {
+    for (int e = tid; e < HQ * 64; e += Z_THREADS) {
       const int r = e / 64, c = e % 64, h = r / a.Q, qi = r % a.Q;
       float acc = 0.f;
       for (int j = 0; j < a.Q; ++j) acc = fmaf(sa[r * SP + a.F + j], a.qkv[((size_t)b * a.Q + j) * a.ldq + 2 * a.inner + h * 64 + c], acc);
       a.olat[((size_t)b * a.Q + qi) * a.inner + h * 64 + c] = acc;
     }
   }
-  // weighted sum over the features for this column tile: thread = (float4 column, row group of 10); tiles double-buffered
-  const int c4 = tid % 24, rg = tid / 24;                  // 24 float4 columns x 10 row groups (240 threads)
-  float4 acc[7];
+  const int cw = c0 + warp * 32;
+  if (cw >= d) return;
+  float acc[2][NT][4];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int buf = 0;
-  for (int f0 = 0; f0 < a.F; f0 += Z_FT, buf ^= 1) {
-    if (f0 + Z_FT < a.F) load_tile(buf ^ 1, f0 + Z_FT);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    if (rg < 10) {
-      const int nf = a.F - f0 < Z_FT ? a.F - f0 : Z_FT;
-      const float* tile = sx + buf * Z_FT * (Z_CT + 4);
-      for (int fl = 0; fl < nf; ++fl) {
-        const float4 xv = *reinterpret_cast<const float4*>(tile + fl * (Z_CT + 4) + c4 * 4);
+  for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          const int r = rg + 10 * k;
-          if (r < HQ) {
-            const float p = sa[r * SP + f0 + fl];
-            acc[k].x = fmaf(p, xv.x, acc[k].x); acc[k].y = fmaf(p, xv.y, acc[k].y); acc[k].z = fmaf(p, xv.z, acc[k].z); acc[k].w = fmaf(p, xv.w, acc[k].w);
-          }
-        }
+    for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+  const float* xp = a.xhat + (size_t)b * a.F * d + cw + 4 * g;
+  const uint32_t* bh = reinterpret_cast<const uint32_t*>(sa) + g * SP + t;
+  const uint32_t* bl = sl + g * SP + t;
+  const int nks = (a.F + 7) / 8;
+  constexpr int Z_PF = 7;                                    // register ring, as in the scores kernel
+  auto xrow = [&](int k) { return reinterpret_cast<const float4*>(xp + (size_t)(k < a.F ? k : a.F - 1) * d); };
+  float4 r1[Z_PF], r2[Z_PF];
+#pragma unroll
+  for (int u = 0; u < Z_PF; ++u) { r1[u] = __ldg(xrow(u * 8 + t)); r2[u] = __ldg(xrow(u * 8 + t + 4)); }
+  for (int ks0 = 0; ks0 < nks; ks0 += Z_PF) {
+#pragma unroll
+    for (int u = 0; u < Z_PF; ++u) {
+      const int ks = ks0 + u;
+      if (ks >= nks) break;
+      const int k1 = ks * 8 + t, k2 = k1 + 4;               // keys past F contribute nothing (alpha forced to 0 below)
+      const float4 v1 = r1[u], v2 = r2[u];
+      if (ks + Z_PF < nks) { r1[u] = __ldg(xrow(k1 + 8 * Z_PF)); r2[u] = __ldg(xrow(k2 + 8 * Z_PF)); }
+      uint32_t ah0[4], al0[4], ah1[4], al1[4];
+      tf32_split(v1.x, ah0[0], al0[0]); tf32_split(v1.y, ah0[1], al0[1]); tf32_split(v2.x, ah0[2], al0[2]); tf32_split(v2.y, ah0[3], al0[3]);
+      tf32_split(v1.z, ah1[0], al1[0]); tf32_split(v1.w, ah1[1], al1[1]); tf32_split(v2.z, ah1[2], al1[2]); tf32_split(v2.w, ah1[3], al1[3]);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const uint32_t h0 = k1 < a.F ? bh[n * 8 * SP + ks * 8] : 0u, h1 = k2 < a.F ? bh[n * 8 * SP + ks * 8 + 4] : 0u;
+        const uint32_t l0 = k1 < a.F ? bl[n * 8 * SP + ks * 8] : 0u, l1 = k2 < a.F ? bl[n * 8 * SP + ks * 8 + 4] : 0u;
+        mma_3x(acc[0][n], ah0, al0, h0, h1, l0, l1);
+        mma_3x(acc[1][n], ah1, al1, h0, h1, l0, l1);
       }
     }
-    __syncthreads();
   }
-  cp_async_wait<0>();
-  if (rg < 10) {
+  // accumulator (m-tile m, n-tile n): rows g / g+8 are columns cw + 4g + 2m (+1), columns 2t (+1) are the query rows r
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int r = rg + 10 * k;
-      if (r < HQ) {
-        const size_t row = (size_t)(r / a.Q) * a.Mp + (size_t)b * a.Q + r % a.Q;
-        const float o[4] = {acc[k].x, acc[k].y, acc[k].z, acc[k].w};
-        __nv_bfloat16 hi[4], lo[4];
+  for (int n = 0; n < NT; ++n) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) split_bf16(o[t], hi[t], lo[t]);
-        __nv_bfloat16* po = a.z16 + row * 2 * d + c0 + c4 * 4;
-        *reinterpret_cast<uint2*>(po) = *reinterpret_cast<uint2*>(hi);
-        *reinterpret_cast<uint2*>(po + d) = *reinterpret_cast<uint2*>(lo);
-      }
+    for (int i = 0; i < 2; ++i) {
+      const int r = n * 8 + 2 * t + i;
+      if (r >= HQ) continue;
+      const size_t row = (size_t)(r / a.Q) * a.Mp + (size_t)b * a.Q + r % a.Q;
+      const float o[4] = {acc[0][n][i], acc[0][n][2 + i], acc[1][n][i], acc[1][n][2 + i]};
+      __align__(8) __nv_bfloat16 hi[4];
+      __align__(8) __nv_bfloat16 lo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split_bf16(o[u], hi[u], lo[u]);
+      __nv_bfloat16* po = a.z16 + row * 2 * d + cw + 4 * g;
+      *reinterpret_cast<uint2*>(po) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(po + d) = *reinterpret_cast<const uint2*>(lo);
     }
+  }
+}
+
+template <int NT>
+inline cudaError_t attn_configure_nt(size_t ss, size_t zs) {
+  cudaError_t e = cudaFuncSetAttribute(perceiver_scores_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(perceiver_softmax_z_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs);
+}
+inline cudaError_t attn_configure(int HQ, size_t ss, size_t zs) {
+  switch (attn_nt(HQ)) {
+    case 1: return attn_configure_nt<1>(ss, zs);
+    case 2: return attn_configure_nt<2>(ss, zs);
+    case 3: return attn_configure_nt<3>(ss, zs);
+    case 4: return attn_configure_nt<4>(ss, zs);
+    case 6: return attn_configure_nt<6>(ss, zs);
+    default: return attn_configure_nt<8>(ss, zs);
+  }
+}
+template <int NT>
+inline void attn_launch_nt(const ScoreArgs& sa, const ZArgs& za, cudaStream_t st) {
+  const int HQ = sa.H * sa.Q;
+  launch_pdl(perceiver_scores_kernel<NT>, dim3((sa.F + SC_FPC - 1) / SC_FPC, sa.B), dim3(SC_THREADS), score_smem_bytes(HQ, sa.d), st, sa);
+  launch_pdl(perceiver_softmax_z_kernel<NT>, dim3((sa.d + Z_CT - 1) / Z_CT, sa.B), dim3(Z_THREADS), z_smem_bytes(HQ, sa.F, sa.Q), st, za);
+}
+inline void attn_launch(const ScoreArgs& sa, const ZArgs& za, cudaStream_t st) {
+  switch (attn_nt(sa.H * sa.Q)) {
+    case 1: attn_launch_nt<1>(sa, za, st); break;
+    case 2: attn_launch_nt<2>(sa, za, st); break;
+    case 3: attn_launch_nt<3>(sa, za, st); break;
+    case 4: attn_launch_nt<4>(sa, za, st); break;
+    case 6: attn_launch_nt<6>(sa, za, st); break;
+    default: attn_launch_nt<8>(sa, za, st); break;
   }
 }
 

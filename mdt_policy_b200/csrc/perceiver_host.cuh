@@ -146,8 +146,7 @@ MDTB200_API int mdtb200_perceiver_create(const MdtPerceiverConfig* cfg, MdtPerce
   const size_t D = d, I = h->inner, FF = h->ff, HQ = (size_t)h->H * h->Q;
   const size_t ss = pr::score_smem_bytes((int)HQ, d), zs = pr::z_smem_bytes((int)HQ, cfg->max_features, h->Q);
   if (ss > 200 * 1024 || zs > 200 * 1024) { pfail(h, MDTB200_EUNSUPPORTED, "max_features %d too large for the attention kernels", cfg->max_features); return bail(MDTB200_EUNSUPPORTED); }
-  if (cudaFuncSetAttribute(pr::perceiver_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss) != cudaSuccess ||
-      cudaFuncSetAttribute(pr::perceiver_softmax_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs) != cudaSuccess) {
+  if (pr::attn_configure((int)HQ, ss, zs) != cudaSuccess) {
     pfail(h, MDTB200_ECUDA, "perceiver attention kernels need %zu / %zu bytes of shared memory", ss, zs); return bail(MDTB200_ECUDA);
   }
   int rc = 0;
@@ -259,11 +258,9 @@ MDTB200_API int mdtb200_perceiver_forward(MdtPerceiver* h, const float* x_f, con
     }
     {
       pr::ScoreArgs a{h->qt, h->cq, h->xhat, h->scores, B, F, Fp, Q, H, Mp, d};
-      launch_pdl(pr::perceiver_scores_kernel, dim3((F + pr::SC_CH - 1) / pr::SC_CH, B), dim3(256), pr::score_smem_bytes(HQ, d), st, a);
-      TRY(pcheck(h, "perceiver_scores_kernel"));
       pr::ZArgs z{h->scores, h->qkv, 3 * I, I, h->xhat, h->z16, h->wsum, h->olat, B, F, Fp, Q, H, Mp, d};
-      launch_pdl(pr::perceiver_softmax_z_kernel, dim3(d / pr::Z_CT, B), dim3(256), pr::z_smem_bytes(HQ, F, Q), st, z);
-      TRY(pcheck(h, "perceiver_softmax_z_kernel"));
+      pr::attn_launch(a, z, st);
+      TRY(pcheck(h, "perceiver attention kernels"));
     }
     {   // Wv_h (g (.) z_h) : head-grouped GEMM, N = 64
       tc::TcGemm t{};

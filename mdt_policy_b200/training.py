@@ -27,6 +27,19 @@ ACT_GELU, ACT_MISH, ACT_SILU = 1, 2, 3
 # whenever the shapes allow it (reduce and output-column dims multiples of 64); MDTB200_TRAIN_TC=0 forces the exact-fp32
 # CUDA-core GEMMs everywhere (the 7-wide action embedding / output head always use them).
 USE_TC = os.environ.get("MDTB200_TRAIN_TC", "1") != "0"
+# One autograd node per residual branch with operand-emitting kernels (training_fused.py) whenever the architecture allows it
+# (embed_dim multiple of 128 and <= 512, projection dims multiples of 64); MDTB200_TRAIN_FUSED=0 keeps the per-primitive graph below.
+USE_FUSED = USE_TC and os.environ.get("MDTB200_TRAIN_FUSED", "1") != "0"
+
+
+def _fused(net):
+    if not USE_FUSED or not net.action_emb.weight.is_cuda:     # CPU tensors: the primitives below raise "no CPU fallback"
+        return None
+    ok = net.__dict__.get("_train_fused_ok")
+    from . import training_fused
+    if ok is None:
+        ok = net.__dict__["_train_fused_ok"] = training_fused.eligible(net)
+    return training_fused if ok else None
 
 
 def _gemm(mode, A, B, bias, Cout, M, N, K):
@@ -288,6 +301,9 @@ def _mask_goal(net, goals):
 
 def encode_train(net, states, goals):
     """forward_enc_only with gradients (mdtv_transformer.py:213-222 / mdt_transformer.py:211-229)."""
+    fused = _fused(net)
+    if fused is not None:
+        return fused.encode_train(net, states, goals)
     if goals.dim() == 2:
         goals = goals[:, None, :]
     goals = _mask_goal(net, goals)
@@ -314,6 +330,9 @@ def encode_train(net, states, goals):
 
 def decode_train(net, ctx, actions, sigma):
     """forward_dec_only with gradients (mdtv_transformer.py:224-236, ConditionedBlock :292-309)."""
+    fused = _fused(net)
+    if fused is not None:
+        return fused.decode_train(net, ctx, actions, sigma)
     d = net.embed_dim
     half = d // 2
     e = sigma.float().log() / 4
@@ -338,6 +357,9 @@ def decode_train(net, ctx, actions, sigma):
 
 
 def forward_train(net, states, actions, goals, sigma):
+    fused = _fused(net)
+    if fused is not None:
+        return fused.forward_train(net, states, actions, goals, sigma)
     ctx = encode_train(net, states, goals)
     net.latent_encoder_emb = ctx
     return decode_train(net, ctx, _c(actions.float()), sigma)
