@@ -231,6 +231,7 @@ MDTB200_API int mdtb200_op_gemm16(int mode, const void* A16, const void* B16, co
                                   int epi, int splits, float* sk_ws, unsigned* sk_cnt, void* stream);
 MDTB200_API int mdtb200_op_ln_fwd16(const float* x, const float* w, const float* b, const float* shift, const float* scale, int mod_stride,
                                     int rows_per_group, int M, int d, float* y, void* y16, void* stream);
+MDTB200_API int mdtb200_op_ln_bwd2_partials(int M, int T);   /* rows of the [.., 2d] partial buffer mdtb200_op_ln_bwd2 fills */
 MDTB200_API int mdtb200_op_ln_bwd2(const float* x, const float* dy, const float* w, const float* b, const float* scale, int mod_stride,
                                    const float* dres, float* dx, float* dshift, float* dscale, int dmod_stride, float* partial, int M, int d,
                                    int T, void* stream);

@@ -45,6 +45,7 @@ struct TcGemm {
   // split-K (deterministic): grid.z = splits CTAs per tile write fp32 partial tiles to sk_ws, the last one to arrive (sk_cnt, self-
   // resetting counters, one per tile, zeroed once by the owner) adds them in slice order and runs the epilogue.
   int splits; float* sk_ws; unsigned* sk_cnt;
+  int bn_hint;                      // 0: tile-width policy of launch_tc_gemm; 64 / 128 / 192: use this width when it divides N
 };
 
 struct TcParams {
@@ -580,6 +581,7 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
     static const int ov_d = getenv("MDTB200_BN_D") ? atoi(getenv("MDTB200_BN_D")) : 0;
     static const int ov_w = getenv("MDTB200_BN_WIDE") ? atoi(getenv("MDTB200_BN_WIDE")) : 0;
     const int ov = g.N >= 1024 ? ov_w : ov_d;
+    if (g.bn_hint && g.N % g.bn_hint == 0) bn = g.bn_hint;
     if ((ov == 64 || ov == 128 || ov == 192) && g.N % ov == 0) bn = ov;
   }
   CUtensorMap ta, tw;

@@ -483,6 +483,12 @@ __global__ void __launch_bounds__(128) attention_fixed_kernel(AttnArgs a) {
     const float inv = 1.0f / sum;
 #pragma unroll
     for (int j = 0; j < TK; ++j) row[j] *= inv;
+    if (a.p_drop > 0.f) {     // training: same mask stream as attention_kernel / attention_bwd_kernel, index ((b H + h) Tq + i) Tk + j
+      const int hg = blockIdx.y * HC + tid / TQ, i = tid % TQ;
+      const unsigned long long base = (((unsigned long long)b * a.H + hg) * TQ + i) * TK;
+#pragma unroll
+      for (int j = 0; j < TK; ++j) row[j] *= dropout_scale(a.seed, base + j, a.p_drop);
+    }
   }
   __syncthreads();
   // P.V: each thread produces 4 consecutive output columns of one query row

@@ -229,6 +229,130 @@ __global__ void __launch_bounds__(256) ln_bwd2_kernel(LnBwd2Args a) {
   }
 }
 
+// Row-parallel variant of the kernel above (one warp per ROW, CTA = R = T * groups-per-CTA <= 16 rows): the per-row terms of the
+// parameter / modulation gradients meet in shared memory and are summed in row order (deterministic).  partial = [ceil(M / R), 2d].
+template <int VPL>
+__global__ void __launch_bounds__(512) ln_bwd3_kernel(LnBwd2Args a, int R) {
+  extern __shared__ __align__(16) float lnb_smem[];            // [R][2d]
+  constexpr int d = VPL * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * R + warp;
+  const bool live = row < a.M;
+  float4 t1[VPL], t2[VPL], u1[VPL], u2[VPL];                   // (dn xhat | dn) and (dy | dy n)
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) t1[i] = t2[i] = u1[i] = u2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const int g = row / a.T;
+    const float* xr = a.x + (size_t)row * d;
+    const float* dyr = a.dy + (size_t)row * d;
+    float4 v[VPL], dy4[VPL], wv4[VPL], bv4[VPL], sc4[VPL], dr4[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      dy4[i] = *reinterpret_cast<const float4*>(dyr + c);
+      wv4[i] = *reinterpret_cast<const float4*>(a.w + c);
+      bv4[i] = a.b ? *reinterpret_cast<const float4*>(a.b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sc4[i] = a.scale ? *reinterpret_cast<const float4*>(a.scale + (size_t)g * a.mod_stride + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      dr4[i] = a.dres ? *reinterpret_cast<const float4*>(a.dres + (size_t)row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+    float sg = 0.f, sgx = 0.f;
+    float4 gq[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float xh[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      const float dyv[4] = {dy4[i].x, dy4[i].y, dy4[i].z, dy4[i].w}, scv[4] = {sc4[i].x, sc4[i].y, sc4[i].z, sc4[i].w};
+      const float wv[4] = {wv4[i].x, wv4[i].y, wv4[i].z, wv4[i].w}, bv[4] = {bv4[i].x, bv4[i].y, bv4[i].z, bv4[i].w};
+      float dn[4], gw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dn[j] = dyv[j] * scv[j];
+        gw[j] = dn[j] * wv[j];
+        sg += gw[j]; sgx += gw[j] * xh[j];
+      }
+      t1[i] = make_float4(dn[0] * xh[0], dn[1] * xh[1], dn[2] * xh[2], dn[3] * xh[3]);
+      t2[i] = make_float4(dn[0], dn[1], dn[2], dn[3]);
+      u1[i] = dy4[i];
+      u2[i] = make_float4(dyv[0] * (xh[0] * wv[0] + bv[0]), dyv[1] * (xh[1] * wv[1] + bv[1]), dyv[2] * (xh[2] * wv[2] + bv[2]), dyv[3] * (xh[3] * wv[3] + bv[3]));
+      gq[i] = make_float4(gw[0], gw[1], gw[2], gw[3]);
+      v[i] = make_float4(xh[0], xh[1], xh[2], xh[3]);
+    }
+    const float mg = warp_sum(sg) / (float)d, mgx = warp_sum(sgx) / (float)d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(a.dx + (size_t)row * d + c) =
+          make_float4(dr4[i].x + rstd * (gq[i].x - mg - v[i].x * mgx), dr4[i].y + rstd * (gq[i].y - mg - v[i].y * mgx),
+                      dr4[i].z + rstd * (gq[i].z - mg - v[i].z * mgx), dr4[i].w + rstd * (gq[i].w - mg - v[i].w * mgx));
+    }
+  }
+  float* mine = lnb_smem + (size_t)warp * 2 * d;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(mine + c) = t1[i];
+    *reinterpret_cast<float4*>(mine + d + c) = t2[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += lnb_smem[(size_t)r * 2 * d + c];
+    a.partial[(size_t)blockIdx.x * 2 * d + c] = s;
+  }
+  if (a.dshift) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(mine + c) = u1[i];
+      *reinterpret_cast<float4*>(mine + d + c) = u2[i];
+    }
+    __syncthreads();
+    const int gpc = R / a.T, G = a.M / a.T;
+    for (int e = threadIdx.x; e < gpc * 2 * d; e += blockDim.x) {
+      const int gl = e / (2 * d), c = e % (2 * d), g = blockIdx.x * gpc + gl;
+      if (g >= G) continue;
+      float s = 0.f;
+      for (int t = 0; t < a.T; ++t) s += lnb_smem[(size_t)(gl * a.T + t) * 2 * d + c];
+      if (c < d) a.dshift[(size_t)g * a.dmod_stride + c] = s;
+      else a.dscale[(size_t)g * a.dmod_stride + c - d] = s;
+    }
+  }
+}
+
+// out[g, c] (+)= sum_{t < T, g*T + t < rows} src[(g*T + t), c]: block = 32 columns x 8 row lanes, lanes summed in fixed order
+__global__ void __launch_bounds__(256) group_sum2_kernel(const float* __restrict__ src, float* __restrict__ out, int G, int T, int C, int rows, int accumulate) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx, g = blockIdx.y;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    const int t1 = min(T, rows - g * T);
+    const float* p = src + (size_t)g * T * C + c;
+    int t = ty;
+    for (; t + 24 < t1; t += 32) { s0 += p[(size_t)t * C]; s1 += p[(size_t)(t + 8) * C]; s2 += p[(size_t)(t + 16) * C]; s3 += p[(size_t)(t + 24) * C]; }
+    for (; t < t1; t += 8) s0 += p[(size_t)t * C];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][tx];
+    out[(size_t)g * C + c] = accumulate ? out[(size_t)g * C + c] + s : s;
+  }
+}
+
 // Narrow linear layers (the 7-wide action embedding / output head), M rows:
 //   forward  y[m, j] = sum_k x[m, k] W[j, k] + b[j]   (J <= 8 outputs, warp per row)
 struct NarrowFwdArgs { const float* x; const float* W; const float* bias; float* y; int M, K, J; };

@@ -3,7 +3,7 @@
 // train-mode forward (score_wrappers.py:45-63 -> mdtv_transformer.py:208-236); every FLOP of forward and backward runs in
 // these kernels.  Included by engine.cu (single translation unit).
 #pragma once
-#include "kernels_train.cuh"
+#include "kernels_train2.cuh"
 
 namespace {
 
@@ -134,9 +134,8 @@ MDTB200_API int mdtb200_op_gemm_tc(int mode, const float* A, const float* B, con
 // out[g, c] (+)= sum_t src[g*T + t, c]
 MDTB200_API int mdtb200_op_group_sum(const float* src, float* out, int G, int T, int Cn, int accumulate, void* stream) {
   if (!src || !out || G < 1 || T < 1 || Cn < 1) return op_fail(MDTB200_EINVAL, "op_group_sum: bad argument");
-  const long tot = (long)G * Cn;
-  group_sum_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src, out, G, T, Cn, accumulate);
-  return op_check("group_sum_kernel");
+  group_sum2_kernel<<<dim3((Cn + 31) / 32, G), 256, 0, (cudaStream_t)stream>>>(src, out, G, T, Cn, G * T, accumulate);
+  return op_check("group_sum2_kernel");
 }
 
 // column sum of a tall matrix in two deterministic stages; `scratch` holds ceil(M / 64) * C floats
@@ -144,9 +143,8 @@ MDTB200_API int mdtb200_op_colsum(const float* src, float* out, float* scratch, 
   if (!src || !out || !scratch || M < 1 || Cn < 1) return op_fail(MDTB200_EINVAL, "op_colsum: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int slabs = (M + 63) / 64;
-  colsum_partial_kernel<<<dim3((Cn + 127) / 128, slabs), 128, 0, st>>>(src, scratch, M, Cn, 64);
-  const long tot = Cn;
-  group_sum_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(scratch, out, 1, slabs, Cn, accumulate);
+  group_sum2_kernel<<<dim3((Cn + 31) / 32, slabs), 256, 0, st>>>(src, scratch, slabs, 64, Cn, M, 0);
+  group_sum2_kernel<<<dim3((Cn + 31) / 32, 1), 256, 0, st>>>(scratch, out, 1, slabs, Cn, slabs, accumulate);
   return op_check("colsum kernels");
 }
 

@@ -29,7 +29,7 @@ MDTB200_API int mdtb200_op_split_multi(const void* table, const void* blocks, in
 //   mode 0  C[M,N] = A[M,K] . B[N,K]^T + bias     A16 = x16 [M,2K], B16 = w16 [N,2K]; epi 6 (GELU16): C = pre-activation, C16 [M,2N] = split(GELU(C))
 //   mode 1  C[M,K] = A[M,N] . B[N,K]              A16 = dy16 [M,2N], B16 = w16 [N,2K] read MN-major
 //   mode 2  C[N,K] = A[M,N]^T . B[M,K]            A16 = dy16 [M,2N], B16 = x16 [M,2K], both MN-major; splits > 1: deterministic split-K
-//           over M with workspace sk_ws (splits * ceil(N/128) * ceil(K/64|128) * 128 * BN floats; mdtb200_op_gemm16_ws) and zeroed counters sk_cnt
+//           over M (also accepted by mode 1, over N) with workspace sk_ws (splits * ceil(N/128) * ceil(K/64|128) * 128 * BN floats; mdtb200_op_gemm16_ws) and zeroed counters sk_cnt
 MDTB200_API int64_t mdtb200_op_gemm16_ws(int N, int K, int splits) {
   return (int64_t)splits * ((N + 127) / 128) * ((K + 63) / 64) * 128 * 64;      // tiles x 128 x BN, BN | K-extent: same for BN = 64 / 128 / 192
 }
@@ -49,11 +49,15 @@ MDTB200_API int mdtb200_op_gemm16(int mode, const void* A16, const void* B16, co
   } else if (mode == 1) {
     if (N % 64 || K % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm16: dgrad needs N, K multiples of 64");
     t.lda16 = 2 * N; t.w_mn = 1; t.ldw16 = 2 * K; t.ldc = K; t.M = M; t.N = K; t.K = N;
+    if (splits > 1) { t.splits = splits; t.sk_ws = sk_ws; t.sk_cnt = sk_cnt; }
   } else {
     if (N % 64 || K % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm16: wgrad needs N, K multiples of 64");
     t.a_mn = 1; t.lda16 = 2 * N; t.w_mn = 1; t.ldw16 = 2 * K; t.ldc = K; t.M = N; t.N = K; t.K = M;
     if (splits > 1) { t.splits = splits; t.sk_ws = sk_ws; t.sk_cnt = sk_cnt; }
   }
+  // 128-wide tiles whenever they divide the output: the training GEMMs have M >= 1536 rows, so 64-wide tiles only add waves and
+  // operand re-reads (tools/sweep_train_tiles.sh: 5.84 -> 5.48 ms per graph-replayed step)
+  t.bn_hint = ((t.M + 127) / 128) * (t.N / 128) * (t.splits > 1 ? t.splits : 1) >= 74 ? 128 : 64;      // ... unless that leaves half the SMs idle
   if (g_op_tma.cache.size() > 4096) g_op_tma.cache.clear();
   const char* e = tc::launch_tc_gemm(g_op_tma, t, (cudaStream_t)stream);
   if (e) return op_fail(MDTB200_ECUDA, "op_gemm16: %s", e);
@@ -80,14 +84,37 @@ MDTB200_API int mdtb200_op_ln_fwd16(const float* x, const float* w, const float*
 }
 
 // LayerNorm(+modulate) backward per group of T rows, fused with the residual gradient (dx = dres + ...); dshift / dscale rows
-// (stride dmod_stride) may be NULL; partial = [ceil(G / 8), 2d] (d ln.weight | d ln.bias), finished by mdtb200_op_group_sum
+// (stride dmod_stride) may be NULL; partial = [mdtb200_op_ln_bwd2_partials(M, T), 2d] (d ln.weight | d ln.bias), finished by mdtb200_op_group_sum
+MDTB200_API int mdtb200_op_ln_bwd2_partials(int M, int T) {
+  if (T <= 16 && M % T == 0) { const int R = T * (16 / T); return (M + R - 1) / R; }
+  return ((M + T - 1) / T + 7) / 8;
+}
 MDTB200_API int mdtb200_op_ln_bwd2(const float* x, const float* dy, const float* w, const float* b, const float* scale, int mod_stride,
                                    const float* dres, float* dx, float* dshift, float* dscale, int dmod_stride, float* partial, int M, int d,
                                    int T, void* stream) {
   if (!x || !dy || !w || !dx || !partial || M < 1 || T < 1 || d % 128 != 0 || d > 512) return op_fail(MDTB200_EINVAL, "op_ln_bwd2: bad argument");
   LnBwd2Args a{x, dy, w, b, scale, mod_stride, dres, dx, dshift, dscale, dmod_stride, partial, M, d, T};
-  const int G = (M + T - 1) / T, blocks = (G + 7) / 8;
   cudaStream_t st = (cudaStream_t)stream;
+  if (T <= 16 && M % T == 0) {      // row-parallel kernel: CTA = R rows = whole groups
+    const int R = T * (16 / T), blocks = (M + R - 1) / R;
+    const size_t smem = (size_t)R * 2 * d * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(ln_bwd3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 128 * 4);
+      cudaFuncSetAttribute(ln_bwd3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 256 * 4);
+      cudaFuncSetAttribute(ln_bwd3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 384 * 4);
+      cudaFuncSetAttribute(ln_bwd3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 512 * 4);
+      configured = true;
+    }
+    switch (d / 128) {
+      case 1: ln_bwd3_kernel<1><<<blocks, 32 * R, smem, st>>>(a, R); break;
+      case 2: ln_bwd3_kernel<2><<<blocks, 32 * R, smem, st>>>(a, R); break;
+      case 3: ln_bwd3_kernel<3><<<blocks, 32 * R, smem, st>>>(a, R); break;
+      case 4: ln_bwd3_kernel<4><<<blocks, 32 * R, smem, st>>>(a, R); break;
+    }
+    return op_check("ln_bwd3_kernel");
+  }
+  const int G = (M + T - 1) / T, blocks = (G + 7) / 8;
   switch (d / 128) {
     case 1: ln_bwd2_kernel<1><<<blocks, 256, 0, st>>>(a); break;
     case 2: ln_bwd2_kernel<2><<<blocks, 256, 0, st>>>(a); break;
@@ -106,6 +133,16 @@ MDTB200_API int mdtb200_op_attn_fwd16(const float* q, int ldq, const float* k, c
   AttnArgs a{};
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y16 = static_cast<__nv_bfloat16*>(y16); a.ld16 = 2 * H * hd; a.lo_off = H * hd;
   a.B = B; a.H = H; a.hd = hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal; a.scale = 1.0f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed;
+  // the shipped shapes run the compile-time specialised kernel (2 heads per CTA), as the sampling engine does
+  const bool c = causal != 0;
+  #define ATT_CASE(HD, TQ, TK, CA)                                                                                  \
+    if (hd == HD && Tq == TQ && Tk == TK && c == (CA != 0) && H % 2 == 0) {                                         \
+      attention_fixed_kernel<HD, TQ, TK, CA, 2><<<dim3(B, H / 2), 128, 0, (cudaStream_t)stream>>>(a);               \
+      return op_check("attention_fixed_kernel (16)");                                                               \
+    }
+  ATT_CASE(48, 10, 10, 1) ATT_CASE(48, 10, 4, 1) ATT_CASE(48, 4, 4, 0)
+  ATT_CASE(64, 10, 10, 1) ATT_CASE(64, 10, 3, 1) ATT_CASE(64, 3, 3, 0)
+  #undef ATT_CASE
   const size_t smem = attention_smem_bytes(H * hd, H, Tq, Tk);
   static size_t configured = 0;
   if (smem > configured) {

@@ -61,8 +61,9 @@ class SplitKWorkspace:
         self.cnt = torch.zeros(4096, dtype=torch.int32, device=device)
 
     @classmethod
-    def get(cls, device, floats):
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    def get(cls, device, floats, slot=0):
+        """slot 0: GEMMs on the caller's stream; slot 1: the weight-gradient side stream (they run concurrently)"""
+        key = (slot, device.index if device.index is not None else torch.cuda.current_device())
         inst = cls._inst.get(key)
         if inst is None:
             inst = cls._inst[key] = cls(device)
@@ -73,11 +74,12 @@ class SplitKWorkspace:
         return inst
 
 
-def _pick_splits(N, K, M):
-    tiles = ((N + 127) // 128) * (K // (128 if (K % 128 == 0 and K >= 1024) else 64))
-    nkb = (M + 63) // 64
-    s = max(1, min(8, round(200 / max(tiles, 1)), nkb // 4))
-    return int(s)
+def _pick_splits(rows, cols, reduce):
+    """split-K factor for an output of rows x cols (tiles of 128 x 128|64) reduced over `reduce`: fill ~1.4 waves of the 148 SMs,
+    keep >= 4 k-blocks of 64 per slice"""
+    tiles = ((rows + 127) // 128) * (cols // (128 if cols % 128 == 0 else 64))
+    nkb = (reduce + 63) // 64
+    return int(max(1, min(8, round(200 / max(tiles, 1)), nkb // 4)))
 
 
 def gemm16(mode, a16, b16, M, N, K, bias=None, epi=EPI_NONE, want16=False, splits=None):
@@ -89,13 +91,52 @@ def gemm16(mode, a16, b16, M, N, K, bias=None, epi=EPI_NONE, want16=False, split
     out16 = torch.empty(M, 2 * N, dtype=torch.bfloat16, device=dev) if (want16 or epi == EPI_GELU16) else None
     ws = cnt = None
     s = 1
-    if mode == 2:
-        s = _pick_splits(N, K, M) if splits is None else splits
+    if mode == 2 or (mode == 1 and N >= 2048):       # long reductions with few output tiles: wgrad (over M), dgrad of the stacked groups (over N)
+        s = (_pick_splits(N, K, M) if mode == 2 else _pick_splits(M, K, N)) if splits is None else splits
         if s > 1:
-            w = SplitKWorkspace.get(dev, lib.mdtb200_op_gemm16_ws(N, K, s))
+            w = SplitKWorkspace.get(dev, lib.mdtb200_op_gemm16_ws(N, K, s) if mode == 2 else lib.mdtb200_op_gemm16_ws(M, K, s))
             ws, cnt = w.ws, w.cnt
     _chk(lib.mdtb200_op_gemm16(mode, _p(a16), _p(b16), _p(bias), _p(out), _p(out16), M, N, K, epi, s, _p(ws), _p(cnt), _stream(a16)), "op_gemm16")
     return (out, out16) if out16 is not None else out
+
+
+# Weight-gradient GEMMs have no consumer inside the backward pass, so they run on a side stream next to the (latency-bound) chain of
+# input-gradient kernels of the same residual branch and are joined before the branch's backward returns (autograd / DDP hooks see
+# finished gradients).  MDTB200_TRAIN_WGRAD_STREAM=0 keeps everything on one stream.
+import os as _os
+_WGRAD_SIDE = _os.environ.get("MDTB200_TRAIN_WGRAD_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def wgrad_begin(dy16, x16, M, N, K):
+    """dW (N, K) = dy16^T . x16, launched on the side stream; call wgrad_join(device) before the result leaves the backward."""
+    if not _WGRAD_SIDE:
+        return gemm16(2, dy16, x16, M, N, K)
+    dev = dy16.device
+    lib = _lib.load()
+    out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    s = _pick_splits(N, K, M)
+    ws = cnt = None
+    if s > 1:
+        w = SplitKWorkspace.get(dev, lib.mdtb200_op_gemm16_ws(N, K, s), slot=1)
+        ws, cnt = w.ws, w.cnt
+    side = _side(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    _chk(lib.mdtb200_op_gemm16(2, _p(dy16), _p(x16), None, _p(out), None, M, N, K, EPI_NONE, s, _p(ws), _p(cnt), C.c_void_p(side.cuda_stream)), "op_gemm16 (wgrad)")
+    return out
+
+
+def wgrad_join(dev):
+    if _WGRAD_SIDE:
+        torch.cuda.current_stream(dev).wait_stream(_side(dev))
 
 
 def ln_fwd16(x, w, b, shift, scale, mod_stride, T, want32=False):
@@ -110,14 +151,21 @@ def ln_fwd16(x, w, b, shift, scale, mod_stride, T, want32=False):
 def ln_bwd2(x, dy, w, b, scale, mod_stride, dres, dshift, dscale, dmod_stride, T):
     """-> dx (= dres + LN backward), d ln.weight, d ln.bias; dshift / dscale rows are written in place when given."""
     M, d = x.shape
-    G = (M + T - 1) // T
-    nb = (G + 7) // 8
+    nb = _lib.load().mdtb200_op_ln_bwd2_partials(M, T)
     dx = torch.empty_like(x)
     partial = torch.empty(nb, 2 * d, dtype=torch.float32, device=x.device)
     _chk(_lib.load().mdtb200_op_ln_bwd2(_p(x), _p(dy), _p(w), _p(b), _p(scale), mod_stride, _p(dres), _p(dx), _p(dshift), _p(dscale), dmod_stride,
                                         _p(partial), M, d, T, _stream(x)), "op_ln_bwd2")
     wb = group_sum(partial, 1, nb).view(2 * d)
     return dx, wb[:d], (wb[d:] if b is not None else None)
+
+
+def ln_fwd(x, w, b, T=1):
+    """plain fp32 LayerNorm output (final norms)"""
+    M, d = x.shape
+    y = torch.empty_like(x)
+    _chk(_lib.load().mdtb200_op_ln_fwd16(_p(x), _p(w), _p(b), None, None, 0, T, M, d, _p(y), None, _stream(x)), "op_ln_fwd16")
+    return y
 
 
 def attn_fwd16(q, ldq, k, v, ldkv, B, H, hd, Tq, Tk, causal, p_drop, seed):

@@ -101,8 +101,9 @@ class LinearG(Function):
             dy16, db = O.split(dy2, want_colsum=True)
         else:
             dy16, db = O.split(dy2), None
+        dw = O.wgrad_begin(dy16, x16, M, N, K)
         dx = O.gemm16(1, dy16, bank.w16[name], M, N, K).view(xshape) if ctx.needs_input_grad[0] else None
-        dw = O.gemm16(2, dy16, x16, M, N, K)
+        O.wgrad_join(dy16.device)
         gw = [dw[a:b] for a, b in rows]
         gb = [db[a:b] for a, b in rows] if has_bias else []
         return (dx, None, None, None, *gw, *gb)
@@ -153,8 +154,8 @@ class AttnBranch(Function):
         has_bo, has_bi = bank.bias[n_o] is not None, bank.bias[n_in] is not None
         r = O.res_drop_bwd(dout2, f, gate, gate.stride(0) if gate is not None else 0, dgate, 3 * d, Tq, p_res, seed_r, want_bias=has_bo)
         df16, dbo = r if has_bo else (r, None)
+        dwo = O.wgrad_begin(df16, y16, M, d, d)
         dy = O.gemm16(1, df16, bank.w16[n_o], M, d, d)
-        dwo = O.gemm16(2, df16, y16, M, d, d)
         if kv is None:
             dqkv = torch.empty(M, 3 * d, dtype=torch.float32, device=dev)
             O.attn_bwd(qkv, 3 * d, qkv[:, d:], qkv[:, 2 * d:], 3 * d, dy, dqkv, 3 * d, dqkv[:, d:], dqkv[:, 2 * d:], 3 * d, B, H, hd, Tq, Tk,
@@ -169,9 +170,10 @@ class AttnBranch(Function):
             dq16, dbi = O.split(dqkv, want_colsum=True)
         else:
             dq16, dbi = O.split(dqkv), None
+        dwi = O.wgrad_begin(dq16, a16, M, Nin, d)
         da = O.gemm16(1, dq16, bank.w16[n_in], M, Nin, d)
-        dwi = O.gemm16(2, dq16, a16, M, Nin, d)
         dx, dlw, dlb = O.ln_bwd2(x2, da, ln_w, ln_b, scale, scale.stride(0) if scale is not None else 0, dout2, dshift, dscale, 3 * d, Tq)
+        O.wgrad_join(dev)
         n_w = Nin // d
         gw = [dwi[i * d:(i + 1) * d] for i in range(n_w)] + [dwo]
         gb = ([dbi[i * d:(i + 1) * d] for i in range(n_w)] if has_bi else []) + ([dbo] if has_bo else [])
@@ -210,18 +212,38 @@ class MLPBranch(Function):
         has_bp, has_bf = bank.bias[n_proj] is not None, bank.bias[n_fc] is not None
         r = O.res_drop_bwd(dout2, f, gate, gate.stride(0) if gate is not None else 0, dgate, 3 * d, Tq, p_drop, seed, want_bias=has_bp)
         df16, dbp = r if has_bp else (r, None)
+        dwp = O.wgrad_begin(df16, g16, M, d, F)                      # (d, F)
         dg = O.gemm16(1, df16, bank.w16[n_proj], M, d, F)            # (M, F)
-        dwp = O.gemm16(2, df16, g16, M, d, F)                        # (d, F)
         if has_bf:
             dh16, dbf = O.split(dg, h=h, act=O.ACT_GELU, want_colsum=True)
         else:
             dh16, dbf = O.split(dg, h=h, act=O.ACT_GELU), None
+        dwf = O.wgrad_begin(dh16, a16, M, F, d)
         da = O.gemm16(1, dh16, bank.w16[n_fc], M, F, d)
-        dwf = O.gemm16(2, dh16, a16, M, F, d)
         dx, dlw, dlb = O.ln_bwd2(x2, da, ln_w, ln_b, scale, scale.stride(0) if scale is not None else 0, dout2, dshift, dscale, 3 * d, Tq)
+        O.wgrad_join(x2.device)
         grads = [dwf, dwp] + ([dbf] if has_bf else []) + ([dbp] if has_bp else [])
         assert len(grads) == n_params
         return (dx.view(B, Tq, d), dshift, dscale, dgate, None, dlw, dlb, *grads)
+
+
+class FinalNorm(Function):
+    """plain LayerNorm (encoder.ln / decoder.ln) with the partial-sum backward"""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        B, Tq, d = x.shape
+        x2 = T._c(x).view(B * Tq, d)
+        ctx.save_for_backward(x2, w, b)
+        ctx.shape = (B, Tq, d)
+        return O.ln_fwd(x2, w, b).view(B, Tq, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, b = ctx.saved_tensors
+        B, Tq, d = ctx.shape
+        dx, dw, db = O.ln_bwd2(x2, T._c(dy).view(B * Tq, d), w, b, None, 0, None, None, None, 0, Tq)
+        return dx.view(B, Tq, d), dw, db
 
 
 class NarrowIn(Function):
@@ -312,7 +334,7 @@ def encode_train(net, states, goals):
         x = AttnBranch.apply(x, None, None, None, None, cfg, blk.ln_1.weight, blk.ln_1.bias, *_attn_params(a))
         cfg = (bank, f"enc{i}.fc", f"enc{i}.proj", blk.mlp.dropout.p if train else 0.0)
         x = MLPBranch.apply(x, None, None, None, cfg, blk.ln_2.weight, blk.ln_2.bias, *_mlp_params(blk.mlp))
-    return T.LayerNormMod.apply(x, net.encoder.ln.weight, net.encoder.ln.bias, None, None)
+    return FinalNorm.apply(x, net.encoder.ln.weight, net.encoder.ln.bias)
 
 
 def decode_train(net, ctx, actions, sigma):
@@ -345,7 +367,7 @@ def decode_train(net, ctx, actions, sigma):
         x = AttnBranch.apply(x, kvs[i], None, None, None, cfg, blk.ln3.weight, blk.ln3.bias, *_xattn_params(a))
         cfg = (bank, f"dec{i}.fc", f"dec{i}.proj", blk.mlp.dropout.p if train else 0.0)
         x = MLPBranch.apply(x, sh2, s2, g2, cfg, blk.ln_2.weight, blk.ln_2.bias, *_mlp_params(blk.mlp))
-    x = T.LayerNormMod.apply(x, net.decoder.ln.weight, net.decoder.ln.bias, None, None)
+    x = FinalNorm.apply(x, net.decoder.ln.weight, net.decoder.ln.bias)
     return NarrowOut.apply(x, net.action_pred.weight, net.action_pred.bias)
 
 
