@@ -194,9 +194,13 @@ struct SmemLayout {
 };
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <int BN, int PASSES>
+// EXT = true compiles in the training extensions (MN-major operands, split-K with in-kernel reduction, GELU16); the sampling engine
+// runs the EXT = false instantiations, whose code is exactly the lean inference kernel.
+template <int BN, int PASSES, bool EXT = false>
 __global__ void __launch_bounds__((SmemLayout<BN, PASSES>::NT), (SmemLayout<BN, PASSES>::MIN_CTAS))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  const bool a_mn = EXT && p.a_mn, w_mn = EXT && p.w_mn;
+  const int splits = EXT ? p.splits : 1;
   using L = SmemLayout<BN, PASSES>;
   constexpr int NT = L::NT;
   extern __shared__ uint8_t smem_raw[];
@@ -211,21 +215,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int n0w = n0 + (p.wg_rows ? (m0 / p.wg_rows) * p.wg_stride : 0);     // W row of this tile (weight groups, e.g. one per head)
-  const int nkb_all = (p.K + BK - 1) / BK;
-  const int kb_beg = p.splits > 1 ? (int)((long)nkb_all * blockIdx.z / p.splits) : 0;
-  const int kb_end = p.splits > 1 ? (int)((long)nkb_all * (blockIdx.z + 1) / p.splits) : nkb_all;
+  const int nkb_all = EXT ? (p.K + BK - 1) / BK : p.K / BK;
+  const int kb_beg = splits > 1 ? (int)((long)nkb_all * blockIdx.z / splits) : 0;
+  const int kb_end = splits > 1 ? (int)((long)nkb_all * (blockIdx.z + 1) / splits) : nkb_all;
   const int nkb = kb_end - kb_beg;           // k-blocks of this CTA (split-K: a slice of the reduce dimension)
   if (threadIdx.x == 0) TC_STAMP(0);
   // operand tile loads: K-major = one box {64 k, rows}; MN-major = boxes {64 mn, 64 k} (8 KB each) along the MN extent
   auto load_a = [&](uint32_t dst, uint32_t bar, int kb, int lo) {
-    if (!p.a_mn) tma_load_2d(dst, &tmA, bar, (lo ? p.K : 0) + kb * BK, m0);
+    if (!a_mn) tma_load_2d(dst, &tmA, bar, (lo ? p.K : 0) + kb * BK, m0);
     else {
 #pragma unroll
       for (int j = 0; j < BM / 64; ++j) tma_load_2d(dst + j * 8192, &tmA, bar, (lo ? p.a_lo : 0) + m0 + 64 * j, kb * BK);
     }
   };
   auto load_w = [&](uint32_t dst, uint32_t bar, int kb, int lo) {
-    if (!p.w_mn) tma_load_2d(dst, &tmW, bar, (lo ? p.K : 0) + kb * BK, n0w);
+    if (!w_mn) tma_load_2d(dst, &tmW, bar, (lo ? p.K : 0) + kb * BK, n0w);
     else {
 #pragma unroll
       for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * 8192, &tmW, bar, (lo ? p.w_lo : 0) + n0w + 64 * j, kb * BK);
@@ -280,8 +284,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN) | (p.a_mn ? 1u << 15 : 0u) | (p.w_mn ? 1u << 16 : 0u);
-      const uint32_t a_step = p.a_mn ? 2048 >> 4 : (UMMA_K * 2) >> 4, w_step = p.w_mn ? 2048 >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t idesc = make_idesc(BM, BN) | (a_mn ? 1u << 15 : 0u) | (w_mn ? 1u << 16 : 0u);
+      const uint32_t a_step = a_mn ? 2048 >> 4 : (UMMA_K * 2) >> 4, w_step = w_mn ? 2048 >> 4 : (UMMA_K * 2) >> 4;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % L::STAGES;
         const uint32_t ph = (kb / L::STAGES) & 1;
@@ -290,10 +294,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kb == 0) TC_STAMP(2);
         if (kb == nkb - 1) TC_STAMP(3);
         const uint32_t st = sbase + s * L::STAGE;
-        const uint64_t a_hi = p.a_mn ? make_smem_desc_mn(st) : make_smem_desc(st);
-        const uint64_t w_hi = p.w_mn ? make_smem_desc_mn(st + L::A_TILE) : make_smem_desc(st + L::A_TILE);
-        const uint64_t a_lo = p.a_mn ? make_smem_desc_mn(st + L::A_TILE + L::W_TILE) : make_smem_desc(st + L::A_TILE + L::W_TILE);
-        const uint64_t w_lo = p.w_mn ? make_smem_desc_mn(st + 2 * L::A_TILE + L::W_TILE) : make_smem_desc(st + 2 * L::A_TILE + L::W_TILE);
+        const uint64_t a_hi = a_mn ? make_smem_desc_mn(st) : make_smem_desc(st);
+        const uint64_t w_hi = w_mn ? make_smem_desc_mn(st + L::A_TILE) : make_smem_desc(st + L::A_TILE);
+        const uint64_t a_lo = a_mn ? make_smem_desc_mn(st + L::A_TILE + L::W_TILE) : make_smem_desc(st + L::A_TILE + L::W_TILE);
+        const uint64_t w_lo = w_mn ? make_smem_desc_mn(st + 2 * L::A_TILE + L::W_TILE) : make_smem_desc(st + 2 * L::A_TILE + L::W_TILE);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // K-major: +32 bytes per UMMA_K inside the 128-byte swizzle row; MN-major: +16 rows of 128 bytes
@@ -355,18 +359,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]);
-        if (nkb == 0) {
+        if (EXT && nkb == 0) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = 0.f;        // empty split-K slice: nothing was accumulated
         }
-        if (p.bias && p.splits <= 1) {
+        if (p.bias && splits <= 1) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + col + j);
             o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
           }
         }
-        if (p.epi == EPI_GELU && p.splits <= 1) {
+        if (p.epi == EPI_GELU && splits <= 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = gelu_erf_fast(o[j]);
         }
@@ -379,11 +383,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (threadIdx.x == 64) TC_STAMP(6);
     bool finish = true;
-    if (p.splits > 1) {
+    if (EXT && splits > 1) {
       // split-K: publish this slice's raw tile, count arrivals; the last CTA of the tile sums the slices in slice order
       // (deterministic), applies bias / activation and continues into phase B; the others are done.
       const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-      float* ws = p.sk_ws + (size_t)tile * p.splits * (BM * BN);
+      float* ws = p.sk_ws + (size_t)tile * splits * (BM * BN);
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
         const int idx = threadIdx.x + it * NT;
@@ -397,7 +401,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       volatile int* s_last = reinterpret_cast<volatile int*>(smem + L::BAR_OFF + 8 * (2 * L::STAGES + 1) + 8);
       if (threadIdx.x == 0) {
         const unsigned old = atomicAdd(p.sk_cnt + tile, 1u);
-        const int last = old == (unsigned)(p.splits - 1);
+        const int last = old == (unsigned)(splits - 1);
         if (last) p.sk_cnt[tile] = 0u;              // self-reset: the next launch finds the counters zero again
         *s_last = last;
       }
@@ -410,7 +414,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int idx = threadIdx.x + it * NT;
           const int r = idx / GPR, cg = (idx % GPR) * 8;
           float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-          for (int z = 0; z < p.splits; ++z) {
+          for (int z = 0; z < splits; ++z) {
             const float* src = ws + (size_t)z * (BM * BN) + r * BN + cg;
             const float4 a = __ldcg(reinterpret_cast<const float4*>(src)), b = __ldcg(reinterpret_cast<const float4*>(src + 4));
             s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
@@ -469,7 +473,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         *reinterpret_cast<float4*>(cr) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4*>(cr + 4) = make_float4(o[4], o[5], o[6], o[7]);
       }
-      if (p.epi == EPI_GELU16) {
+      if (EXT && p.epi == EPI_GELU16) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) o[t] = gelu_erf_fast(o[t]);
       }
@@ -542,9 +546,9 @@ struct TmaEncoder {
   }
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool EXT = false>
 inline const char* configure_one() {
-  cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN, PASSES>::TOTAL);
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, PASSES, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN, PASSES>::TOTAL);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 inline const char* configure_kernels() {
@@ -555,13 +559,16 @@ inline const char* configure_kernels() {
   if ((e = configure_one<64, 3>())) return e;
   if ((e = configure_one<128, 1>())) return e;
   if ((e = configure_one<64, 1>())) return e;
+  if ((e = configure_one<192, 3, true>())) return e;
+  if ((e = configure_one<128, 3, true>())) return e;
+  if ((e = configure_one<64, 3, true>())) return e;
   return nullptr;
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool EXT = false>
 inline void launch_one(const CUtensorMap& a, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
-  dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.splits > 1 ? p.splits : 1);
-  launch_pdl(tc_gemm_kernel<BN, PASSES>, grid, dim3(THREADS), SmemLayout<BN, PASSES>::TOTAL, st, a, w, p);
+  dim3 grid(p.N / BN, (p.M + BM - 1) / BM, EXT && p.splits > 1 ? p.splits : 1);
+  launch_pdl(tc_gemm_kernel<BN, PASSES, EXT>, grid, dim3(THREADS), SmemLayout<BN, PASSES>::TOTAL, st, a, w, p);
 }
 
 // returns nullptr on success, an error message otherwise
@@ -595,7 +602,10 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
              g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride, g.w_dynamic ? 0 : 1,
              g.a_mn, g.w_mn, g.lda16 / 2, g.ldw16 / 2, g.splits > 1 ? g.splits : 1, g.sk_ws, g.sk_cnt};
-  if (g.passes == 3) {
+  const bool ext = g.a_mn || g.w_mn || g.splits > 1 || g.epi == EPI_GELU16 || g.K % BK != 0;
+  if (ext) {
+    if (bn == 192) launch_one<192, 3, true>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3, true>(ta, tw, p, st); else launch_one<64, 3, true>(ta, tw, p, st);
+  } else if (g.passes == 3) {
     if (bn == 192) launch_one<192, 3>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3>(ta, tw, p, st); else launch_one<64, 3>(ta, tw, p, st);
   } else {
     if (bn == 192) launch_one<192, 1>(ta, tw, p, st); else if (bn == 128) launch_one<128, 1>(ta, tw, p, st); else launch_one<64, 1>(ta, tw, p, st);
