@@ -237,6 +237,11 @@ MDTB200_API int mdtb200_op_ln_bwd2(const float* x, const float* dy, const float*
                                    int T, void* stream);
 MDTB200_API int mdtb200_op_attn_fwd16(const float* q, int ldq, const float* k, const float* v, int ldkv, void* y16, int B, int H, int hd,
                                       int Tq, int Tk, int causal, float p_drop, uint64_t seed, void* stream);
+/* attention backward writing the projections' output gradients as GEMM operands (+ per-sample bias partials); shipped shapes only */
+MDTB200_API int mdtb200_op_attn_bwd16(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dy, int lddy,
+                                      float* dk32, float* dv32, int ldkv32, void* dq16, int wq, int col0q, void* dkv16, int wkv, int col0k,
+                                      int col0v, float* bpart, int bpart_kv, int B, int H, int hd, int Tq, int Tk, int causal, float p_drop,
+                                      uint64_t seed, void* stream);
 MDTB200_API int mdtb200_op_res_drop_fwd(const float* x, const float* f, const float* gate, int gate_stride, float* out, int M, int d, int T,
                                         float p, uint64_t seed, void* stream);
 MDTB200_API int mdtb200_op_res_drop_bwd(const float* dout, const float* f, const float* gate, int gate_stride, void* df16, float* dgate,

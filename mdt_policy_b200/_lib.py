@@ -24,7 +24,7 @@ EXPORTS = [
     "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
     "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout", "mdtb200_op_adamw_ema", "mdtb200_op_set_seed_epoch",
     "mdtb200_op_split", "mdtb200_op_split_rows_per_slab", "mdtb200_op_split_multi", "mdtb200_op_gemm16_ws", "mdtb200_op_gemm16", "mdtb200_op_ln_fwd16",
-    "mdtb200_op_ln_bwd2", "mdtb200_op_ln_bwd2_partials", "mdtb200_op_attn_fwd16", "mdtb200_op_res_drop_fwd", "mdtb200_op_res_drop_bwd", "mdtb200_op_narrow_fwd", "mdtb200_op_narrow_wgrad",
+    "mdtb200_op_ln_bwd2", "mdtb200_op_ln_bwd2_partials", "mdtb200_op_attn_fwd16", "mdtb200_op_attn_bwd16", "mdtb200_op_res_drop_fwd", "mdtb200_op_res_drop_bwd", "mdtb200_op_narrow_fwd", "mdtb200_op_narrow_wgrad",
     "mdtb200_perceiver_create", "mdtb200_perceiver_destroy", "mdtb200_perceiver_last_error", "mdtb200_perceiver_bind_weight",
     "mdtb200_perceiver_commit_weights", "mdtb200_perceiver_forward", "mdtb200_perceiver_launch_count",
 ]
@@ -111,6 +111,9 @@ def _declare(lib):
     lib.mdtb200_op_ln_bwd2_partials.argtypes = [i32, i32]
     lib.mdtb200_op_ln_bwd2_partials.restype = i32
     lib.mdtb200_op_attn_fwd16.argtypes = [vp, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, u64, vp]
+    lib.mdtb200_op_attn_bwd16.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, vp, i32,
+                                          i32, i32, i32, i32, i32, i32, f32, u64, vp]
+    lib.mdtb200_op_attn_bwd16.restype = i32
     lib.mdtb200_op_res_drop_fwd.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]
     lib.mdtb200_op_res_drop_bwd.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]
     lib.mdtb200_op_narrow_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]

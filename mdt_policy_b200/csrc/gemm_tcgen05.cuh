@@ -45,6 +45,7 @@ struct TcGemm {
   // split-K (deterministic): grid.z = splits CTAs per tile write fp32 partial tiles to sk_ws, the last one to arrive (sk_cnt, self-
   // resetting counters, one per tile, zeroed once by the owner) adds them in slice order and runs the epilogue.
   int splits; float* sk_ws; unsigned* sk_cnt;
+  float* colpart;                   // EPI_GELUBWD16: [ceil(M / 128), N] column sums of the emitted operand per row tile (bias gradient partials)
   int bn_hint;                      // 0: tile-width policy of launch_tc_gemm; 64 / 128 / 192: use this width when it divides N
 };
 
@@ -59,6 +60,7 @@ struct TcParams {
   int w_early;                 // 1: W is static (inference weights): its first tiles may be requested before the dependency wait
   int a_mn, w_mn, a_lo, w_lo;  // MN-major operand flags and the column offset of their lo halves
   int splits; float* sk_ws; unsigned* sk_cnt;
+  float* colpart;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -467,6 +469,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
         }
       }
+      if (EXT && p.epi == EPI_GELUBWD16) {     // activation backward fused into the dgrad GEMM: o = dL/dg * GELU'(h), h = p.R
+        const float* hr = p.R + (size_t)row * p.ldr + nb;
+        const float4 h0 = *reinterpret_cast<const float4*>(hr), h1 = *reinterpret_cast<const float4*>(hr + 4);
+        o[0] *= gelu_erf_grad(h0.x); o[1] *= gelu_erf_grad(h0.y); o[2] *= gelu_erf_grad(h0.z); o[3] *= gelu_erf_grad(h0.w);
+        o[4] *= gelu_erf_grad(h1.x); o[5] *= gelu_erf_grad(h1.y); o[6] *= gelu_erf_grad(h1.z); o[7] *= gelu_erf_grad(h1.w);
+        if (p.colpart) {
+          *reinterpret_cast<float4*>(stage + r * SP + cg) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(stage + r * SP + cg + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
       const int orow = p.gi ? (row / p.gi) * p.go + p.goff + row % p.gi : row;
       if (p.C) {
         float* cr = p.C + (size_t)orow * p.ldc + nb;
@@ -485,6 +497,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __nv_bfloat16* ch = p.C16 + (size_t)orow * p.ldc16 + nb;
         *reinterpret_cast<uint4*>(ch) = *reinterpret_cast<const uint4*>(hi);
         *reinterpret_cast<uint4*>(ch + p.lo_off) = *reinterpret_cast<const uint4*>(lo);
+      }
+    }
+    if (EXT && p.epi == EPI_GELUBWD16 && p.colpart && finish) {
+      // column sums of the emitted operand over this tile's rows (rows past M hold zeros: their A rows were zero-filled by TMA)
+      __syncthreads();
+      for (int c = threadIdx.x; c < BN; c += NT) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < BM; ++r) s += stage[r * SP + c];
+        p.colpart[(size_t)blockIdx.y * p.N + n0 + c] = s;
       }
     }
     tc_fence_before();
@@ -577,7 +599,7 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if ((!g.a_mn || !g.w_mn) && g.K % BK != 0) return "unsupported GEMM shape (a K-major operand needs K % 64 == 0)";
   if ((g.a_mn || g.w_mn) && (g.wg_rows || g.passes != 3)) return "MN-major operands: no weight groups, bf16x3 only";
   if (g.splits > 1 && (!g.sk_ws || !g.sk_cnt || g.splits > (g.K + BK - 1) / BK || g.C16 || g.gi)) return "bad split-K configuration";
-  if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE && g.epi != EPI_GELU16) return "unsupported epilogue";
+  if (g.epi != EPI_NONE && g.epi != EPI_GELU && g.epi != EPI_RES && g.epi != EPI_RES_GATE && g.epi != EPI_GELU16 && g.epi != EPI_GELUBWD16) return "unsupported epilogue";
   // tile-N choice (measured, profiles/r01_experiments.md): 128 columns for the wide GEMMs (N >= 1024), 64 for N = d; the
   // 192-column tile turns the fused QKV (N = 1152) into a single wave when a full batch is launched at once (mt >= 16).
   // A "widest tile that still fills ~1 wave, else narrowest" policy was 11 % slower end to end and no better for training.
@@ -601,8 +623,9 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   if (e) return e;
   TcParams p{g.bias, g.C, g.ldc, g.C16, g.ldc16, g.lo_off, g.R, g.ldr, g.gate, g.gate_stride, g.rows_per_group > 0 ? g.rows_per_group : 1,
              g.M, g.N, g.K, g.epi, g.trace, g.gi, g.go, g.goff, g.wg_rows, g.wg_stride, g.w_dynamic ? 0 : 1,
-             g.a_mn, g.w_mn, g.lda16 / 2, g.ldw16 / 2, g.splits > 1 ? g.splits : 1, g.sk_ws, g.sk_cnt};
-  const bool ext = g.a_mn || g.w_mn || g.splits > 1 || g.epi == EPI_GELU16 || g.K % BK != 0;
+             g.a_mn, g.w_mn, g.lda16 / 2, g.ldw16 / 2, g.splits > 1 ? g.splits : 1, g.sk_ws, g.sk_cnt, g.colpart};
+  const bool ext = g.a_mn || g.w_mn || g.splits > 1 || g.epi == EPI_GELU16 || g.epi == EPI_GELUBWD16 || g.K % BK != 0;
+  if (g.epi == EPI_GELUBWD16 && (!g.R || !g.C16 || g.splits > 1)) return "GELUBWD16 needs R (pre-activation), C16, no split-K";
   if (ext) {
     if (bn == 192) launch_one<192, 3, true>(ta, tw, p, st); else if (bn == 128) launch_one<128, 3, true>(ta, tw, p, st); else launch_one<64, 3, true>(ta, tw, p, st);
   } else if (g.passes == 3) {

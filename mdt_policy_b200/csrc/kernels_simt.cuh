@@ -59,6 +59,10 @@ __device__ __forceinline__ void pdl_enter(int tag = KT_OTHER) { pdl_trigger(); p
 // ------------------------------------------------------------------------------------------
 // activations (exact variants, matching ATen)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx gelu_erf (training: activation backward, also fused into the tensor-core GEMM epilogue)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
 // Same function with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. fp32 rounding level): one exp, one
 // division and five FMAs instead of libm's branchy erff -- used in the tensor-core GEMM epilogue where GELU is the
 // largest non-MMA cost.
@@ -99,7 +103,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // Exact fp32 GEMM:  C[M,N] = epi( A[M,K] . W[N,K]^T + bias[N] )
 // 128x64x16 tiles, 256 threads, 8x4 micro-tile per thread, register-prefetched double buffering.
 enum Epi : int { EPI_NONE = 0, EPI_GELU = 1, EPI_MISH = 2, EPI_SILU = 3, EPI_RES = 4, EPI_RES_GATE = 5,
-                 EPI_GELU16 = 6 };   // tcgen05 GEMM only (training): fp32 output = pre-activation, split-bf16 output = GELU of it
+                 EPI_GELU16 = 6,     // tcgen05 GEMM only (training): fp32 output = pre-activation, split-bf16 output = GELU of it
+                 EPI_GELUBWD16 = 7 }; // tcgen05 GEMM only (training): split-bf16 output = acc * GELU'(R), column partial sums of it
 
 struct GemmArgs {
   const float* A; int lda;

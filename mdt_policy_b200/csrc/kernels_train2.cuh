@@ -12,7 +12,7 @@
 namespace mdt {
 
 __device__ __forceinline__ float act_grad(float v, int act) {
-  if (act == ACT_GELU) return 0.5f * (1.0f + erff(v * 0.70710678118654752440f)) + v * 0.39894228040143267794f * expf(-0.5f * v * v);
+  if (act == ACT_GELU) return gelu_erf_grad(v);
   if (act == ACT_SILU) { const float s = 1.0f / (1.0f + expf(-v)); return s * (1.0f + v * (1.0f - s)); }
   const float sp = v > 20.0f ? v : log1pf(expf(v));      // mish
   const float th = tanhf(sp);
@@ -351,6 +351,120 @@ __global__ void __launch_bounds__(256) group_sum2_kernel(const float* __restrict
     for (int r = 0; r < 8; ++r) s += red[r][tx];
     out[(size_t)g * C + c] = accumulate ? out[(size_t)g * C + c] + s : s;
   }
+}
+
+// Attention backward for the shipped tiny shapes, compile-time specialised (one CTA per (sample, head), 128 threads), emitting the
+// projections' output gradients directly as GEMM operands:
+//   P = softmax(q k^T scale + causal top-left mask), P_used = P * dropout mask (same hash stream as the forward kernels)
+//   dV = P_used^T dY ; dP = (dY V^T) * mask ; dS = P (dP - rowsum(dP P)) scale ; dQ = dS K ; dK = dS^T Q     (transformer_blocks.py:119-158)
+// dq goes to dq32 (fp32, row stride ldq32) and/or dq16 (bf16 hi|lo rows of width wq: element (row, col0q + h*HD + c), lo at + wq), the same
+// for dk / dv with (ldkv32, wkv, col0k / col0v); bpart (optional) = [B, wq] per-sample column sums of dq (and of dk / dv when they share
+// the dq16 operand, i.e. self-attention) -> one group_sum over the batch gives the q|k|v bias gradients.
+struct AttnBwd2Args {
+  const float* q; int ldq; const float* k; const float* v; int ldkv; const float* dy; int lddy;
+  float* dq32; int ldq32; float* dk32; float* dv32; int ldkv32;
+  __nv_bfloat16* dq16; int wq; int col0q; __nv_bfloat16* dkv16; int wkv; int col0k; int col0v;
+  float* bpart; int bpart_kv;       // bpart_kv: 1 = dk / dv column sums go to bpart as well (columns col0k / col0v of the same wq-wide row)
+  int B, H; float scale; float p_drop; unsigned long long seed;
+};
+template <int HD, int TQ, int TK, int CAUSAL>
+__global__ void __launch_bounds__(128) attention_bwd2_kernel(AttnBwd2Args a) {
+  constexpr int HP = HD + 4, H4 = HD / 4;
+  __shared__ __align__(16) float sq[TQ * HP], sdy[TQ * HP], sk[TK * HP], sv[TK * HP];
+  __shared__ __align__(16) float so[(TQ > TK ? TQ : TK) * HP];        // staging of an output block for the column sums
+  __shared__ float sp[TQ][TK + 1], sds[TQ][TK + 1], spu[TQ][TK + 1];
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, tid = threadIdx.x;
+  for (int e = tid; e < TQ * H4; e += 128) {
+    const int i = e / H4, c = (e % H4) * 4;
+    *reinterpret_cast<float4*>(sq + i * HP + c) = *reinterpret_cast<const float4*>(a.q + (size_t)(b * TQ + i) * a.ldq + h * HD + c);
+    *reinterpret_cast<float4*>(sdy + i * HP + c) = *reinterpret_cast<const float4*>(a.dy + (size_t)(b * TQ + i) * a.lddy + h * HD + c);
+  }
+  for (int e = tid; e < TK * H4; e += 128) {
+    const int j = e / H4, c = (e % H4) * 4;
+    *reinterpret_cast<float4*>(sk + j * HP + c) = *reinterpret_cast<const float4*>(a.k + (size_t)(b * TK + j) * a.ldkv + h * HD + c);
+    *reinterpret_cast<float4*>(sv + j * HP + c) = *reinterpret_cast<const float4*>(a.v + (size_t)(b * TK + j) * a.ldkv + h * HD + c);
+  }
+  __syncthreads();
+  for (int e = tid; e < TQ * TK; e += 128) {
+    const int i = e / TK, j = e % TK;
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+      const float4 qv = *reinterpret_cast<const float4*>(sq + i * HP + c), kv = *reinterpret_cast<const float4*>(sk + j * HP + c);
+      const float4 gv = *reinterpret_cast<const float4*>(sdy + i * HP + c), vv = *reinterpret_cast<const float4*>(sv + j * HP + c);
+      s = fmaf(qv.x, kv.x, s); s = fmaf(qv.y, kv.y, s); s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
+      dp = fmaf(gv.x, vv.x, dp); dp = fmaf(gv.y, vv.y, dp); dp = fmaf(gv.z, vv.z, dp); dp = fmaf(gv.w, vv.w, dp);
+    }
+    sp[i][j] = (CAUSAL && j > i) ? -INFINITY : s * a.scale;
+    sds[i][j] = dp;
+  }
+  __syncthreads();
+  if (tid < TQ) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) mx = fmaxf(mx, sp[tid][j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) { const float ex = expf(sp[tid][j] - mx); sp[tid][j] = ex; sum += ex; }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+    const unsigned long long base = ((unsigned long long)b * a.H * TQ + (unsigned long long)h * TQ + tid) * TK;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) {
+      sp[tid][j] *= inv;
+      const float m = a.p_drop > 0.f ? dropout_scale(a.seed, base + j, a.p_drop) : 1.0f;
+      spu[tid][j] = sp[tid][j] * m;
+      sds[tid][j] *= m;
+      dot += sds[tid][j] * sp[tid][j];
+    }
+#pragma unroll
+    for (int j = 0; j < TK; ++j) sds[tid][j] = sp[tid][j] * (sds[tid][j] - dot) * a.scale;
+  }
+  __syncthreads();
+  // one output block at a time (dQ, dK, dV): thread = (row, 4 columns); results to global (fp32 and / or split bf16) and to `so`
+  auto emit = [&](int rows, int which) {       // which: 0 dQ, 1 dK, 2 dV
+    for (int e = tid; e < rows * H4; e += 128) {
+      const int r = e / H4, c = (e % H4) * 4;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (which == 0) {
+#pragma unroll
+        for (int j = 0; j < TK; ++j) {
+          const float w = sds[r][j];
+          const float4 x = *reinterpret_cast<const float4*>(sk + j * HP + c);
+          o[0] = fmaf(w, x.x, o[0]); o[1] = fmaf(w, x.y, o[1]); o[2] = fmaf(w, x.z, o[2]); o[3] = fmaf(w, x.w, o[3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+          const float w = which == 1 ? sds[i][r] : spu[i][r];
+          const float4 x = *reinterpret_cast<const float4*>((which == 1 ? sq : sdy) + i * HP + c);
+          o[0] = fmaf(w, x.x, o[0]); o[1] = fmaf(w, x.y, o[1]); o[2] = fmaf(w, x.z, o[2]); o[3] = fmaf(w, x.w, o[3]);
+        }
+      }
+      *reinterpret_cast<float4*>(so + r * HP + c) = make_float4(o[0], o[1], o[2], o[3]);
+      const size_t grow = (size_t)b * (which == 0 ? TQ : TK) + r;
+      if (which == 0) {
+        if (a.dq32) *reinterpret_cast<float4*>(a.dq32 + grow * a.ldq32 + h * HD + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (a.dq16) store_split4(a.dq16 + grow * 2 * a.wq + a.col0q + h * HD + c, a.wq, o);
+      } else {
+        float* d32 = which == 1 ? a.dk32 : a.dv32;
+        if (d32) *reinterpret_cast<float4*>(d32 + grow * a.ldkv32 + h * HD + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (a.dkv16) store_split4(a.dkv16 + grow * 2 * a.wkv + (which == 1 ? a.col0k : a.col0v) + h * HD + c, a.wkv, o);
+      }
+    }
+    if (a.bpart && (which == 0 || a.bpart_kv)) {
+      __syncthreads();
+      for (int c = tid; c < HD; c += 128) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += so[r * HP + c];
+        a.bpart[(size_t)b * a.wq + (which == 0 ? a.col0q : which == 1 ? a.col0k : a.col0v) + h * HD + c] = s;
+      }
+      __syncthreads();
+    }
+  };
+  emit(TQ, 0);
+  emit(TK, 1);
+  emit(TK, 2);
 }
 
 // Narrow linear layers (the 7-wide action embedding / output head), M rows:

@@ -27,7 +27,8 @@ MDTB200_API int mdtb200_op_split_multi(const void* table, const void* blocks, in
 
 // GEMM on pre-split operands (bf16x3 on tcgen05, fp32 accumulate / output):
 //   mode 0  C[M,N] = A[M,K] . B[N,K]^T + bias     A16 = x16 [M,2K], B16 = w16 [N,2K]; epi 6 (GELU16): C = pre-activation, C16 [M,2N] = split(GELU(C))
-//   mode 1  C[M,K] = A[M,N] . B[N,K]              A16 = dy16 [M,2N], B16 = w16 [N,2K] read MN-major
+//   mode 1  C[M,K] = A[M,N] . B[N,K]              A16 = dy16 [M,2N], B16 = w16 [N,2K] read MN-major; epi 7 (GELUBWD16): C16 [M,2K] =
+//           split(acc * GELU'(h)) with h passed in the bias slot and the [ceil(M/128), K] column partials of it in C (no fp32 output)
 //   mode 2  C[N,K] = A[M,N]^T . B[M,K]            A16 = dy16 [M,2N], B16 = x16 [M,2K], both MN-major; splits > 1: deterministic split-K
 //           over M (also accepted by mode 1, over N) with workspace sk_ws (splits * ceil(N/128) * ceil(K/64|128) * 128 * BN floats; mdtb200_op_gemm16_ws) and zeroed counters sk_cnt
 MDTB200_API int64_t mdtb200_op_gemm16_ws(int N, int K, int splits) {
@@ -35,7 +36,7 @@ MDTB200_API int64_t mdtb200_op_gemm16_ws(int N, int K, int splits) {
 }
 MDTB200_API int mdtb200_op_gemm16(int mode, const void* A16, const void* B16, const float* bias, float* C, void* C16, int M, int N, int K,
                                   int epi, int splits, float* sk_ws, unsigned* sk_cnt, void* stream) {
-  if (!A16 || !B16 || !C || M < 1 || N < 1 || K < 1 || mode < 0 || mode > 2) return op_fail(MDTB200_EINVAL, "op_gemm16: bad argument");
+  if (!A16 || !B16 || (!C && epi != EPI_GELUBWD16) || M < 1 || N < 1 || K < 1 || mode < 0 || mode > 2) return op_fail(MDTB200_EINVAL, "op_gemm16: bad argument");
   if (const char* e = op_tc_init()) return op_fail(MDTB200_ECUDA, "op_gemm16: %s", e);
   tc::TcGemm t{};
   t.A16 = static_cast<const __nv_bfloat16*>(A16); t.W16 = static_cast<const __nv_bfloat16*>(B16);
@@ -49,6 +50,13 @@ MDTB200_API int mdtb200_op_gemm16(int mode, const void* A16, const void* B16, co
   } else if (mode == 1) {
     if (N % 64 || K % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm16: dgrad needs N, K multiples of 64");
     t.lda16 = 2 * N; t.w_mn = 1; t.ldw16 = 2 * K; t.ldc = K; t.M = M; t.N = K; t.K = N;
+    if (epi == EPI_GELUBWD16) {
+      // activation backward fused into the epilogue: `bias` carries the pre-activation h [M, K] of the forward, `C` the [ceil(M/128), K]
+      // column partials (bias gradient; may be NULL), C16 [M, 2K] receives split(acc * GELU'(h)); nothing is written in fp32
+      if (!bias || !C16 || splits > 1) return op_fail(MDTB200_EINVAL, "op_gemm16: GELUBWD16 needs h (bias slot), C16 and no split-K");
+      t.epi = EPI_GELUBWD16; t.R = bias; t.ldr = K; t.bias = nullptr; t.colpart = C; t.C = nullptr;
+      t.C16 = static_cast<__nv_bfloat16*>(C16); t.ldc16 = 2 * K; t.lo_off = K;
+    } else if (epi != EPI_NONE) return op_fail(MDTB200_EINVAL, "op_gemm16: epilogue %d", epi);
     if (splits > 1) { t.splits = splits; t.sk_ws = sk_ws; t.sk_cnt = sk_cnt; }
   } else {
     if (N % 64 || K % 64) return op_fail(MDTB200_EUNSUPPORTED, "op_gemm16: wgrad needs N, K multiples of 64");
@@ -151,6 +159,29 @@ MDTB200_API int mdtb200_op_attn_fwd16(const float* q, int ldq, const float* k, c
   }
   attention_kernel<<<B, ATT_THREADS, smem, (cudaStream_t)stream>>>(a);
   return op_check("attention_kernel (16)");
+}
+
+// attention backward emitting operands (see attention_bwd2_kernel): shipped shapes only (MDTB200_EUNSUPPORTED otherwise: use mdtb200_op_attn_bwd
+// + mdtb200_op_split).  Self-attention: dq16 = dkv16 = the (M, 2*3D) operand of the fused q|k|v projection (col0 = 0, D, 2D), bpart = (B, 3D).
+// Cross-attention: dq16 = (M, 2D) operand of the query projection, dk32 / dv32 = fp32 halves of the (B*Tk, 2D) context gradient.
+MDTB200_API int mdtb200_op_attn_bwd16(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dy, int lddy,
+                                      float* dk32, float* dv32, int ldkv32, void* dq16, int wq, int col0q, void* dkv16, int wkv, int col0k,
+                                      int col0v, float* bpart, int bpart_kv, int B, int H, int hd, int Tq, int Tk, int causal, float p_drop,
+                                      uint64_t seed, void* stream) {
+  if (!q || !k || !v || !dy || !dq16 || B < 1 || H < 1 || !(p_drop >= 0.f && p_drop < 1.f)) return op_fail(MDTB200_EINVAL, "op_attn_bwd16: bad argument");
+  AttnBwd2Args a{q, ldq, k, v, ldkv, dy, lddy, nullptr, 0, dk32, dv32, ldkv32, static_cast<__nv_bfloat16*>(dq16), wq, col0q,
+                 static_cast<__nv_bfloat16*>(dkv16), wkv, col0k, col0v, bpart, bpart_kv, B, H, 1.0f / sqrtf((float)hd), p_drop, seed};
+  const bool c = causal != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  #define ATTB_CASE(HD, TQ, TK, CA)                                                             \
+    if (hd == HD && Tq == TQ && Tk == TK && c == (CA != 0)) {                                   \
+      attention_bwd2_kernel<HD, TQ, TK, CA><<<B * H, 128, 0, st>>>(a);                          \
+      return op_check("attention_bwd2_kernel");                                                 \
+    }
+  ATTB_CASE(48, 10, 10, 1) ATTB_CASE(48, 10, 4, 1) ATTB_CASE(48, 4, 4, 0)
+  ATTB_CASE(64, 10, 10, 1) ATTB_CASE(64, 10, 3, 1) ATTB_CASE(64, 3, 3, 0)
+  #undef ATTB_CASE
+  return op_fail(MDTB200_EUNSUPPORTED, "op_attn_bwd16: shape (hd %d, Tq %d, Tk %d, causal %d) is not specialised", hd, Tq, Tk, causal);
 }
 
 // out = x + gate[row / T] * dropout(f; p, seed)        (gate NULL: 1; p == 0: identity mask)

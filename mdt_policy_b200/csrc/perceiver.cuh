@@ -71,6 +71,14 @@ __global__ void perceiver_fold_kernel(const float* __restrict__ Wv, const float*
   wvx[(size_t)(h * 64 + c) * 2 * d + m] = hi; wvx[(size_t)(h * 64 + c) * 2 * d + d + m] = lo;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Score path in exact fp32 (the softmax can be saturated: score errors are amplified, value errors are not).  CTA = (16 latent
 // rows, head h):   q_h = scale * lhat Wq_h^T,  k_h = lhat Wk_h^T   (written to the qkv buffer for the latent-key scores),
 //                  qtilde_h = g (.) Wk_h^T q_h  (the query in feature space),  cq = q_h . (Wk_h b)
@@ -85,39 +93,49 @@ constexpr int QP_ROWS = 16, QP_MC = 16;   // static shared memory stays under 48
 template <int D>
 __global__ void __launch_bounds__(256) perceiver_qpath_kernel(QPathArgs a) {
   __shared__ __align__(16) float sl[QP_ROWS][D + 4];
-  __shared__ __align__(16) float sw[128][QP_MC + 4];       // rows 0..63: Wq_h chunk, 64..127: Wk_h chunk
-  __shared__ float sqk[QP_ROWS][128];                      // q_h (scaled) | k_h
+  __shared__ __align__(16) float sw[2][128][QP_MC + 4];    // double-buffered weight chunk: rows 0..63 Wq_h, 64..127 Wk_h (cp.async)
+  float (*sqk)[128] = reinterpret_cast<float (*)[128]>(&sw[0][0][0]);     // q_h (scaled) | k_h: reuses the chunk buffers after step 1
+  static_assert(sizeof(float) * QP_ROWS * 128 <= sizeof(sw), "sqk must fit into the chunk buffers");
   pdl_enter();
   const int r0 = blockIdx.x * QP_ROWS, h = blockIdx.y, tid = threadIdx.x;
+  auto load_chunk = [&](int buf, int m0) {
+    for (int e = tid; e < 128 * (QP_MC / 4); e += 256) {
+      const int wr = e / (QP_MC / 4), mc = (e % (QP_MC / 4)) * 4;
+      const float* W = wr < 64 ? a.Wq : a.Wk;
+      cp_async16(&sw[buf][wr][mc], W + (size_t)(h * 64 + (wr & 63)) * D + m0 + mc);
+    }
+  };
+  load_chunk(0, 0);
+  cp_async_commit();
   for (int e = tid; e < QP_ROWS * (D / 4); e += 256) {
     const int r = e / (D / 4), c = (e % (D / 4)) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + r < a.Mq) v = *reinterpret_cast<const float4*>(a.lhat + (size_t)(r0 + r) * D + c);
     *reinterpret_cast<float4*>(&sl[r][c]) = v;
   }
-  // step 1: thread = (output column c of [q | k], row group of 8)
+  // step 1: thread = (output column c of [q | k], row group of 8); the next weight chunk streams in while this one is consumed
   const int c = tid & 127, rg = tid >> 7;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (int m0 = 0; m0 < D; m0 += QP_MC) {
+  int buf = 0;
+  for (int m0 = 0; m0 < D; m0 += QP_MC, buf ^= 1) {
+    if (m0 + QP_MC < D) load_chunk(buf ^ 1, m0 + QP_MC);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    for (int e = tid; e < 128 * (QP_MC / 4); e += 256) {
-      const int wr = e / (QP_MC / 4), mc = (e % (QP_MC / 4)) * 4;
-      const float* W = wr < 64 ? a.Wq : a.Wk;
-      *reinterpret_cast<float4*>(&sw[wr][mc]) = *reinterpret_cast<const float4*>(W + (size_t)(h * 64 + (wr & 63)) * D + m0 + mc);
-    }
-    __syncthreads();
-#pragma unroll 4
+#pragma unroll
     for (int m = 0; m < QP_MC; m += 4) {
-      const float4 w = *reinterpret_cast<const float4*>(&sw[c][m]);
+      const float4 w = *reinterpret_cast<const float4*>(&sw[buf][c][m]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float4 l = *reinterpret_cast<const float4*>(&sl[rg * 8 + k][m0 + m]);
         acc[k] = fmaf(l.x, w.x, acc[k]); acc[k] = fmaf(l.y, w.y, acc[k]); acc[k] = fmaf(l.z, w.z, acc[k]); acc[k] = fmaf(l.w, w.w, acc[k]);
       }
     }
+    __syncthreads();                 // everyone is done with `buf` before the iteration after next refills it
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int r = rg * 8 + k;
@@ -151,10 +169,6 @@ __global__ void __launch_bounds__(256) perceiver_qpath_kernel(QPathArgs a) {
 
 // ---- warp-level tensor-core helpers for the two passes over xhat (3xTF32: fp32 operands split into tf32 hi + lo, three
 // mma.sync.m16n8k8 per product with fp32 accumulation -> ~2^-21 relative operand error, i.e. fp32-grade scores) ----
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));

@@ -160,41 +160,77 @@ class GraphedTrainStep:
     capture time (as for any CUDA graph); parameters without a gradient at capture time stay frozen.
     """
 
-    def __init__(self, model, optimizer: FusedAdamWEMA, state_images, goal, actions, noise, sigma, modality="lang", warmup=3):
+    def __init__(self, model, optimizer: FusedAdamWEMA, state_images, goal, actions, noise, sigma, modality="lang", warmup=3,
+                 process_group=None, data_parallel=None):
+        """data_parallel (default: torch.distributed is initialised with world_size > 1): gradients are averaged over the process
+        group between two graphs -- [loss + backward + flatten] | one NCCL all-reduce of the flat gradient buffer | [unflatten + fused
+        AdamW/EMA] -- which is DistributedDataParallel's arithmetic with a single bucket; parameters are broadcast from rank 0 first."""
         if not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs FusedAdamWEMA(capturable=True)")
+        import torch.distributed as dist
         dev = actions.device
         self.model, self.opt, self.modality = model, optimizer, modality
+        self.pg = process_group
+        self.dp = (dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1) if data_parallel is None else bool(data_parallel)
+        self.comm = True                  # set False to time the step without the all-reduce (exposed communication = difference)
         self.static = [t.detach().clone() for t in (state_images, goal, actions, noise, sigma)]
         lib = _lib.load()
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         if lib.mdtb200_op_set_seed_epoch(C.c_void_p(self.epoch.data_ptr())) != 0:
             raise RuntimeError("mdtb200_op_set_seed_epoch failed: " + lib.mdtb200_last_error(None).decode())
+        if self.dp:
+            for p in model.parameters():
+                dist.broadcast(p.data, 0, group=process_group)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._body()
+                self._fwd_bwd()
+                if self.dp:
+                    self._allreduce_eager()
+                self.opt.step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
+        if not self.dp:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+                self.opt.step()
+            return
         with torch.cuda.graph(self.graph):
-            self.loss = self._body()
+            self.loss = self._fwd_bwd()
+            self.grads = [p.grad for group in optimizer.param_groups for p in group["params"] if p.grad is not None]
+            self.flat = torch.cat([g.reshape(-1) for g in self.grads])
+        self.graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
+            torch._foreach_copy_(self.grads, [v.view_as(g) for v, g in zip(self.flat.split([g.numel() for g in self.grads]), self.grads)])
+            self.opt.step()
 
-    def _body(self):
+    def _fwd_bwd(self):
         s, g, a, n, sig = self.static
         self.opt.zero_grad(set_to_none=True)
         self.epoch.add_(1)
         loss, _ = self.model.loss({"state_images": s, "modality": self.modality}, a, g, n, sig)
         loss.backward()
-        self.opt.step()
         return loss.detach()
+
+    def _allreduce_eager(self):
+        import torch.distributed as dist
+        grads = [p.grad for group in self.opt.param_groups for p in group["params"] if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg)
+        torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
     def __call__(self, state_images, goal, actions, noise, sigma):
         for dst, src in zip(self.static, (state_images, goal, actions, noise, sigma)):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        if self.dp:
+            if self.comm:
+                import torch.distributed as dist
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.pg)
+            self.graph2.replay()
         return self.loss
 
     def close(self):

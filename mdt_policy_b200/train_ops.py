@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 ACT_GELU, ACT_MISH, ACT_SILU = 1, 2, 3
-EPI_NONE, EPI_GELU16 = 0, 6
+EPI_NONE, EPI_GELU16, EPI_GELUBWD16 = 0, 6, 7
 
 
 def _p(t):
@@ -139,6 +139,18 @@ def wgrad_join(dev):
         torch.cuda.current_stream(dev).wait_stream(_side(dev))
 
 
+def dgrad_gelu_bwd16(dy16, w16, h, M, N, K, want_colsum=False):
+    """dh16 (M, 2K) = split((dy16 . w16) * GELU'(h)) in ONE GEMM (activation backward in the epilogue) [+ its column sums = bias gradient]"""
+    lib = _lib.load()
+    out16 = torch.empty(M, 2 * K, dtype=torch.bfloat16, device=dy16.device)
+    mt = (M + 127) // 128
+    part = torch.empty(mt, K, dtype=torch.float32, device=dy16.device) if want_colsum else None
+    _chk(lib.mdtb200_op_gemm16(1, _p(dy16), _p(w16), _p(h), _p(part), _p(out16), M, N, K, EPI_GELUBWD16, 1, None, None, _stream(dy16)), "op_gemm16 (gelu bwd)")
+    if want_colsum:
+        return out16, group_sum(part, 1, mt).view(K)
+    return out16
+
+
 def ln_fwd16(x, w, b, shift, scale, mod_stride, T, want32=False):
     """x (M, d) -> split-bf16 LayerNorm(+modulate) output (M, 2d) [and the fp32 one]."""
     M, d = x.shape
@@ -178,6 +190,34 @@ def attn_fwd16(q, ldq, k, v, ldkv, B, H, hd, Tq, Tk, causal, p_drop, seed):
 def attn_bwd(q, ldq, k, v, ldkv, dy, dq, lddq, dk, dv, lddkv, B, H, hd, Tq, Tk, causal, p_drop, seed):
     _chk(_lib.load().mdtb200_op_attn_bwd(_p(q), ldq, _p(k), _p(v), ldkv, _p(dy), H * hd, _p(dq), lddq, _p(dk), _p(dv), lddkv, B, H, hd, Tq, Tk,
                                          int(causal), float(p_drop), seed, _stream(q)), "op_attn_bwd")
+
+
+ATTN_BWD16_SHAPES = {(48, 10, 10, True), (48, 10, 4, True), (48, 4, 4, False), (64, 10, 10, True), (64, 10, 3, True), (64, 3, 3, False)}
+
+
+def attn_bwd16_self(qkv, dy, B, H, hd, T, causal, p_drop, seed, want_bias):
+    """self-attention backward -> dqkv16 (M, 2*3D) operand of the fused q|k|v projection [+ (3D,) bias gradient]"""
+    D = H * hd
+    M = B * T
+    d16 = torch.empty(M, 6 * D, dtype=torch.bfloat16, device=qkv.device)
+    part = torch.empty(B, 3 * D, dtype=torch.float32, device=qkv.device) if want_bias else None
+    _chk(_lib.load().mdtb200_op_attn_bwd16(_p(qkv), 3 * D, _p(qkv[:, D:]), _p(qkv[:, 2 * D:]), 3 * D, _p(dy), D, None, None, 0, _p(d16), 3 * D, 0,
+                                           _p(d16), 3 * D, D, 2 * D, _p(part), 1, B, H, hd, T, T, int(causal), float(p_drop), seed, _stream(qkv)),
+         "op_attn_bwd16")
+    return d16, (group_sum(part, 1, B).view(3 * D) if want_bias else None)
+
+
+def attn_bwd16_cross(q, kv, dy, B, H, hd, Tq, Tk, causal, p_drop, seed, want_bias):
+    """cross-attention backward -> dq16 (M, 2D) operand of the query projection, dkv (B, Tk, 2D) fp32 [+ (D,) query bias gradient]"""
+    D = H * hd
+    M = B * Tq
+    d16 = torch.empty(M, 2 * D, dtype=torch.bfloat16, device=q.device)
+    dkv = torch.empty(B, Tk, 2 * D, dtype=torch.float32, device=q.device)
+    part = torch.empty(B, D, dtype=torch.float32, device=q.device) if want_bias else None
+    _chk(_lib.load().mdtb200_op_attn_bwd16(_p(q), D, _p(kv), _p(kv[..., D:]), kv.stride(1), _p(dy), D, _p(dkv), _p(dkv[..., D:]), 2 * D, _p(d16), D, 0,
+                                           None, 0, 0, 0, _p(part), 0, B, H, hd, Tq, Tk, int(causal), float(p_drop), seed, _stream(q)),
+         "op_attn_bwd16")
+    return d16, dkv, (group_sum(part, 1, B).view(D) if want_bias else None)
 
 
 def res_drop_fwd(x, f, gate, gate_stride, T, p, seed):

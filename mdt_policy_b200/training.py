@@ -299,14 +299,24 @@ def _mask_goal(net, goals):
     return goals
 
 
+def _prep_goal_train(net, states, goals):
+    """preprocess_goals in train mode (mdtv_transformer.py:246-258 / mdt_transformer.py:293-305): (B, d) -> (B, 1, d), first goal token
+    when one goal per state step is given, vision-goal truncation to obs_dim, then the Bernoulli goal mask."""
+    if goals.dim() == 2:
+        goals = goals[:, None, :]
+    if goals.shape[1] == net._states_length(states) and net.goal_seq_len == 1:
+        goals = goals[:, :1, :]
+    if goals.shape[-1] == 2 * net.obs_dim:
+        goals = goals[:, :, : net.obs_dim]
+    return _mask_goal(net, goals)
+
+
 def encode_train(net, states, goals):
     """forward_enc_only with gradients (mdtv_transformer.py:213-222 / mdt_transformer.py:211-229)."""
     fused = _fused(net)
     if fused is not None:
         return fused.encode_train(net, states, goals)
-    if goals.dim() == 2:
-        goals = goals[:, None, :]
-    goals = _mask_goal(net, goals)
+    goals = _prep_goal_train(net, states, goals)
     train = net.training
     lang = net.use_modality_encoder and states.get("modality") == "lang" and net._variant == "mdtv"
     gm = net.lang_emb if lang else net.goal_emb
@@ -317,8 +327,9 @@ def encode_train(net, states, goals):
         st = _lin(net.tok_emb, states["static"].float())
         gr = _lin(net.incam_embed, states["gripper"].float())
         s = torch.cat((st, gr), dim=1)
-        g = g + net.pos_emb[:, : net.goal_seq_len, :]
-        s = s + net.pos_emb[:, net.goal_seq_len: net.goal_seq_len + 1, :]
+        # apply_position_embeddings, mdt_transformer.py:317-323: embedding dropout (embed_pdrob) after the position embedding
+        g = _drop(g + net.pos_emb[:, : net.goal_seq_len, :], net.drop.p if train else 0.0)
+        s = _drop(s + net.pos_emb[:, net.goal_seq_len: net.goal_seq_len + 1, :], net.drop.p if train else 0.0)
     x = torch.cat([g, s], dim=1).contiguous()
     for blk in net.encoder.blocks:          # Block.forward, transformer_blocks.py:209-214
         a = LayerNormMod.apply(x, blk.ln_1.weight, blk.ln_1.bias, None, None)

@@ -156,20 +156,28 @@ class AttnBranch(Function):
         df16, dbo = r if has_bo else (r, None)
         dwo = O.wgrad_begin(df16, y16, M, d, d)
         dy = O.gemm16(1, df16, bank.w16[n_o], M, d, d)
+        fast = (hd, Tq, Tk, bool(causal)) in O.ATTN_BWD16_SHAPES      # specialised kernel: emits the operand + bias partials itself
         if kv is None:
-            dqkv = torch.empty(M, 3 * d, dtype=torch.float32, device=dev)
-            O.attn_bwd(qkv, 3 * d, qkv[:, d:], qkv[:, 2 * d:], 3 * d, dy, dqkv, 3 * d, dqkv[:, d:], dqkv[:, 2 * d:], 3 * d, B, H, hd, Tq, Tk,
-                       causal, p_attn, seed_a)
-            dkv, Nin = None, 3 * d
+            Nin, dkv = 3 * d, None
+            if fast:
+                dq16, dbi = O.attn_bwd16_self(qkv, dy, B, H, hd, Tq, causal, p_attn, seed_a, has_bi)
+            else:
+                dqkv = torch.empty(M, 3 * d, dtype=torch.float32, device=dev)
+                O.attn_bwd(qkv, 3 * d, qkv[:, d:], qkv[:, 2 * d:], 3 * d, dy, dqkv, 3 * d, dqkv[:, d:], dqkv[:, 2 * d:], 3 * d, B, H, hd, Tq, Tk,
+                           causal, p_attn, seed_a)
         else:
-            dqkv = torch.empty(M, d, dtype=torch.float32, device=dev)
-            dkv = torch.empty(B, Tk, 2 * d, dtype=torch.float32, device=dev)
-            O.attn_bwd(qkv, d, kv, kv[..., d:], kv.stride(1), dy, dqkv, d, dkv, dkv[..., d:], 2 * d, B, H, hd, Tq, Tk, causal, p_attn, seed_a)
             Nin = d
-        if has_bi:
-            dq16, dbi = O.split(dqkv, want_colsum=True)
-        else:
-            dq16, dbi = O.split(dqkv), None
+            if fast:
+                dq16, dkv, dbi = O.attn_bwd16_cross(qkv, kv, dy, B, H, hd, Tq, Tk, causal, p_attn, seed_a, has_bi)
+            else:
+                dqkv = torch.empty(M, d, dtype=torch.float32, device=dev)
+                dkv = torch.empty(B, Tk, 2 * d, dtype=torch.float32, device=dev)
+                O.attn_bwd(qkv, d, kv, kv[..., d:], kv.stride(1), dy, dqkv, d, dkv, dkv[..., d:], 2 * d, B, H, hd, Tq, Tk, causal, p_attn, seed_a)
+        if not fast:
+            if has_bi:
+                dq16, dbi = O.split(dqkv, want_colsum=True)
+            else:
+                dq16, dbi = O.split(dqkv), None
         dwi = O.wgrad_begin(dq16, a16, M, Nin, d)
         da = O.gemm16(1, dq16, bank.w16[n_in], M, Nin, d)
         dx, dlw, dlb = O.ln_bwd2(x2, da, ln_w, ln_b, scale, scale.stride(0) if scale is not None else 0, dout2, dshift, dscale, 3 * d, Tq)
@@ -213,11 +221,12 @@ class MLPBranch(Function):
         r = O.res_drop_bwd(dout2, f, gate, gate.stride(0) if gate is not None else 0, dgate, 3 * d, Tq, p_drop, seed, want_bias=has_bp)
         df16, dbp = r if has_bp else (r, None)
         dwp = O.wgrad_begin(df16, g16, M, d, F)                      # (d, F)
-        dg = O.gemm16(1, df16, bank.w16[n_proj], M, d, F)            # (M, F)
+        # dL/dh = (df . Wproj) * GELU'(h): the activation backward, the operand split and the c_fc bias-gradient partials all happen in the
+        # dgrad GEMM's epilogue (no fp32 (M, F) gradient is ever written)
         if has_bf:
-            dh16, dbf = O.split(dg, h=h, act=O.ACT_GELU, want_colsum=True)
+            dh16, dbf = O.dgrad_gelu_bwd16(df16, bank.w16[n_proj], h, M, d, F, want_colsum=True)
         else:
-            dh16, dbf = O.split(dg, h=h, act=O.ACT_GELU), None
+            dh16, dbf = O.dgrad_gelu_bwd16(df16, bank.w16[n_proj], h, M, d, F), None
         dwf = O.wgrad_begin(dh16, a16, M, F, d)
         da = O.gemm16(1, dh16, bank.w16[n_fc], M, F, d)
         dx, dlw, dlb = O.ln_bwd2(x2, da, ln_w, ln_b, scale, scale.stride(0) if scale is not None else 0, dout2, dshift, dscale, 3 * d, Tq)
@@ -311,9 +320,7 @@ def encode_train(net, states, goals):
     bank = _bank(net)
     bank.refresh()
     net.__dict__["_train_bank_fresh"] = True
-    if goals.dim() == 2:
-        goals = goals[:, None, :]
-    goals = T._mask_goal(net, goals)
+    goals = T._prep_goal_train(net, states, goals)
     train = net.training
     lang = net.use_modality_encoder and states.get("modality") == "lang" and net._variant == "mdtv"
     gm = net.lang_emb if lang else net.goal_emb
@@ -324,8 +331,8 @@ def encode_train(net, states, goals):
         st = T._lin(net.tok_emb, states["static"].float())
         gr = T._lin(net.incam_embed, states["gripper"].float())
         s = torch.cat((st, gr), dim=1)
-        g = g + net.pos_emb[:, : net.goal_seq_len, :]
-        s = s + net.pos_emb[:, net.goal_seq_len: net.goal_seq_len + 1, :]
+        g = T._drop(g + net.pos_emb[:, : net.goal_seq_len, :], net.drop.p if train else 0.0)
+        s = T._drop(s + net.pos_emb[:, net.goal_seq_len: net.goal_seq_len + 1, :], net.drop.p if train else 0.0)
     x = torch.cat([g, s], dim=1).contiguous()
     H = net.n_heads
     for i, blk in enumerate(net.encoder.blocks):

@@ -136,3 +136,22 @@ def test_generic_sampler_loops_match_oracle_on_cpu_callable():
             got = gcs.SAMPLERS[name](model, state, inp["x_T"], inp["goal"], sig)
             want = orc.sample(P, cfg, state, inp["x_T"], inp["goal"], sig, name)
             assert (got - want).abs().max() < 1e-5, name
+
+
+def test_train_goal_preprocessing_follows_reference_rules():
+    """preprocess_goals in train mode (mdt_transformer.py:293-305): 2-D goals get a token axis, one-goal-per-state-step inputs keep the
+    first token, concatenated vision goals (2 * obs_dim) are truncated, goal_drop masks element-wise only while training"""
+    from mdt_policy_b200 import GCDenoiser, training
+    net = GCDenoiser(H.mdt_inner_cfg(n_enc_layers=1, n_dec_layers=1, goal_drop=0.5), sigma_data=0.5).inner_model
+    states = {"static": torch.zeros(4, 1, 512), "gripper": torch.zeros(4, 1, 512)}
+    net.eval()
+    g = torch.randn(4, 512)
+    assert training._prep_goal_train(net, states, g).shape == (4, 1, 512)
+    assert torch.equal(training._prep_goal_train(net, states, g)[:, 0], g)                     # eval: no mask
+    g2 = torch.randn(4, 1, 1024)
+    assert torch.equal(training._prep_goal_train(net, states, g2), g2[:, :, :512])           # 2 * obs_dim -> obs_dim
+    net.train()
+    torch.manual_seed(0)
+    m = training._prep_goal_train(net, states, torch.ones(64, 512))
+    frac = float((m == 0).float().mean())
+    assert 0.4 < frac < 0.6 and set(m.unique().tolist()) == {0.0, 1.0}

@@ -140,6 +140,60 @@ def test_ddp_two_gpu_gradients_are_rank_means_and_weights_stay_in_sync():
         assert c0 == c1                        # identical weights on both ranks after the fused optimizer step
 
 
+def _graphed_dp_worker(rank, world, port, ret):
+    """data-parallel GraphedTrainStep: [fwd + bwd] graph | one NCCL all-reduce | [fused AdamW/EMA] graph, vs an eager loop that averages
+    the two ranks' gradients by hand (dropout off so both are deterministic)"""
+    import torch.distributed as dist
+    from mdt_policy_b200.optim import GraphedTrainStep
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        cfg = H.mdtv_inner_cfg(2, 2, attn_pdrop=0.0, resid_pdrop=0.0, mlp_pdrop=0.0)
+        inp = {k: v.cuda(rank) for k, v in synthetic_inputs(16, seed=60 + rank).items()}
+        sig = torch.exp(torch.linspace(2.0, -3.0, 16)).cuda(rank)
+        args = (inp["state_images"], inp["goal"], inp["actions"], inp["noise"], sig)
+        # eager reference: 3 warm-up steps + the 3 replays below, gradients averaged over the ranks by hand
+        model = H.build_product(cfg, 15, "trained", device=f"cuda:{rank}").train()
+        opt = FusedAdamWEMA(model.parameters(), lr=2e-4, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.99)
+        for _ in range(3 + 3):
+            opt.zero_grad(set_to_none=True)
+            loss, _ = model.loss({"state_images": args[0], "modality": "lang"}, args[2], args[1], args[3], args[4])
+            loss.backward()
+            for p in model.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad /= world
+            opt.step()
+        want = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        model2 = H.build_product(cfg, 15, "trained", device=f"cuda:{rank}").train()
+        opt2 = FusedAdamWEMA(model2.parameters(), lr=2e-4, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.99, capturable=True)
+        step = GraphedTrainStep(model2, opt2, *args)
+        assert step.dp
+        for _ in range(3):
+            step(*args)
+        torch.cuda.synchronize()
+        got = torch.cat([p.detach().reshape(-1) for p in model2.parameters()])
+        chk = got.double().sum().reshape(1)
+        both = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(both, chk)
+        ret[rank] = (float((got - want).abs().max()), float(want.abs().max()), float(both[0]), float(both[1]))
+        step.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_graphed_data_parallel_step_two_gpus_matches_hand_averaged_eager_steps():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_graphed_dp_worker, args=(2, 29535, ret), nprocs=2, join=True)
+    for rank in (0, 1):
+        err, scale, c0, c1 = ret[rank]
+        assert err < 2e-5 * max(1.0, scale), (err, scale)     # same weights as the eager loop (different summation order in the flat all-reduce)
+        assert c0 == c1                                        # and bit-identical across the ranks
+
+
 def test_graphed_train_step_matches_eager_steps_and_redraws_dropout():
     """CUDA-graph replay of (loss fwd + bwd + fused AdamW/EMA): without dropout the replayed steps reproduce the eager steps'
     losses; with dropout every replay draws new masks (device-side RNG epoch) and the loss still goes down."""

@@ -153,3 +153,42 @@ def test_narrow_linear_ops():
     a = torch.randn(M, J, device="cuda")
     g = torch.randn(M, d, device="cuda")
     assert _rel(O.narrow_wgrad(g, a, True), g.double().t() @ a.double()) < 1e-5            # d action_emb.weight (d, J)
+
+
+@pytest.mark.parametrize("M", [5120, 200])
+def test_dgrad_with_gelu_backward_epilogue(M):
+    """dh16 = split((dy . W) * GELU'(h)) and its column sums, produced by ONE GEMM (mode 1, epilogue 7)"""
+    O = _ops()
+    torch.manual_seed(7)
+    N, K = 384, 1536                     # c_proj: dy (M, d), W (d, 4d) -> dg (M, 4d)
+    dy, w, h = torch.randn(M, N, device="cuda"), torch.randn(N, K, device="cuda") / N ** 0.5, torch.randn(M, K, device="cuda")
+    dh16, cs = O.dgrad_gelu_bwd16(O.split(dy), O.split(w), h, M, N, K, want_colsum=True)
+    hh = h.double().requires_grad_(True)
+    (g,) = torch.autograd.grad(torch.nn.functional.gelu(hh).sum(), hh)
+    ref = (dy.double() @ w.double()) * g
+    assert _rel(_join(dh16), ref) < 3e-5
+    assert _rel(cs, ref.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_attention_backward_emitting_operands_matches_generic_kernel(p):
+    """attention_bwd2_kernel (specialised, writes dqkv16 + bias partials) vs attention_bwd_kernel + split on the same inputs / dropout seed"""
+    O = _ops()
+    torch.manual_seed(8)
+    B, H, hd, T = 33, 8, 48, 10
+    D = H * hd
+    qkv, dy = torch.randn(B * T, 3 * D, device="cuda"), torch.randn(B * T, D, device="cuda")
+    ref = torch.empty_like(qkv)
+    O.attn_bwd(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, dy, ref, 3 * D, ref[:, D:], ref[:, 2 * D:], 3 * D, B, H, hd, T, T, True, p, 1234)
+    d16, bias = O.attn_bwd16_self(qkv, dy, B, H, hd, T, True, p, 1234, True)
+    assert _rel(_join(d16), ref) < 2e-5
+    assert _rel(bias, ref.double().sum(0)) < 1e-5
+    # cross shape: 10 queries x 4 context tokens, strided k/v views of a wider buffer
+    Tk = 4
+    q = torch.randn(B * T, D, device="cuda")
+    kv_all = torch.randn(B, Tk, 8 * D, device="cuda")
+    kv = kv_all[..., 2 * D:4 * D]
+    rq, rkv = torch.empty_like(q), torch.empty(B, Tk, 2 * D, device="cuda")
+    O.attn_bwd(q, D, kv, kv[..., D:], kv.stride(1), dy, rq, D, rkv, rkv[..., D:], 2 * D, B, H, hd, T, Tk, True, p, 77)
+    dq16, dkv, bq = O.attn_bwd16_cross(q, kv, dy, B, H, hd, T, Tk, True, p, 77, True)
+    assert _rel(_join(dq16), rq) < 2e-5 and _rel(dkv, rkv) < 1e-5 and _rel(bq, rq.double().sum(0)) < 1e-5
