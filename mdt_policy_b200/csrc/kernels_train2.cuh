@@ -330,9 +330,10 @@ __global__ void __launch_bounds__(512) ln_bwd3_kernel(LnBwd2Args a, int R) {
   }
 }
 
-// out[g, c] (+)= sum_{t < T, g*T + t < rows} src[(g*T + t), c]: block = 32 columns x 8 row lanes, lanes summed in fixed order
-__global__ void __launch_bounds__(256) group_sum2_kernel(const float* __restrict__ src, float* __restrict__ out, int G, int T, int C, int rows, int accumulate) {
-  __shared__ float red[8][33];
+// out[g, c] (+)= sum_{t < T, g*T + t < rows} src[(g*T + t), c]: block = 32 columns x RL row lanes, lanes summed in fixed order
+template <int RL>
+__global__ void __launch_bounds__(32 * RL) group_sum2_kernel(const float* __restrict__ src, float* __restrict__ out, int G, int T, int C, int rows, int accumulate) {
+  __shared__ float red[RL][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx, g = blockIdx.y;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -340,17 +341,24 @@ __global__ void __launch_bounds__(256) group_sum2_kernel(const float* __restrict
     const int t1 = min(T, rows - g * T);
     const float* p = src + (size_t)g * T * C + c;
     int t = ty;
-    for (; t + 24 < t1; t += 32) { s0 += p[(size_t)t * C]; s1 += p[(size_t)(t + 8) * C]; s2 += p[(size_t)(t + 16) * C]; s3 += p[(size_t)(t + 24) * C]; }
-    for (; t < t1; t += 8) s0 += p[(size_t)t * C];
+    for (; t + 3 * RL < t1; t += 4 * RL) {
+      s0 += p[(size_t)t * C]; s1 += p[(size_t)(t + RL) * C]; s2 += p[(size_t)(t + 2 * RL) * C]; s3 += p[(size_t)(t + 3 * RL) * C];
+    }
+    for (; t < t1; t += RL) s0 += p[(size_t)t * C];
   }
   red[ty][tx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (ty == 0 && c < C) {
     float s = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) s += red[r][tx];
+    for (int r = 0; r < RL; ++r) s += red[r][tx];
     out[(size_t)g * C + c] = accumulate ? out[(size_t)g * C + c] + s : s;
   }
+}
+inline void launch_group_sum2(const float* src, float* out, int G, int T, int C, int rows, int accumulate, cudaStream_t st) {
+  const dim3 grid((C + 31) / 32, G);
+  if (T > 64) group_sum2_kernel<32><<<grid, 1024, 0, st>>>(src, out, G, T, C, rows, accumulate);      // long columns: 32 row lanes
+  else group_sum2_kernel<8><<<grid, 256, 0, st>>>(src, out, G, T, C, rows, accumulate);
 }
 
 // Attention backward for the shipped tiny shapes, compile-time specialised (one CTA per (sample, head), 128 threads), emitting the

@@ -134,7 +134,7 @@ MDTB200_API int mdtb200_op_gemm_tc(int mode, const float* A, const float* B, con
 // out[g, c] (+)= sum_t src[g*T + t, c]
 MDTB200_API int mdtb200_op_group_sum(const float* src, float* out, int G, int T, int Cn, int accumulate, void* stream) {
   if (!src || !out || G < 1 || T < 1 || Cn < 1) return op_fail(MDTB200_EINVAL, "op_group_sum: bad argument");
-  group_sum2_kernel<<<dim3((Cn + 31) / 32, G), 256, 0, (cudaStream_t)stream>>>(src, out, G, T, Cn, G * T, accumulate);
+  launch_group_sum2(src, out, G, T, Cn, G * T, accumulate, (cudaStream_t)stream);
   return op_check("group_sum2_kernel");
 }
 
@@ -143,8 +143,8 @@ MDTB200_API int mdtb200_op_colsum(const float* src, float* out, float* scratch, 
   if (!src || !out || !scratch || M < 1 || Cn < 1) return op_fail(MDTB200_EINVAL, "op_colsum: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int slabs = (M + 63) / 64;
-  group_sum2_kernel<<<dim3((Cn + 31) / 32, slabs), 256, 0, st>>>(src, scratch, slabs, 64, Cn, M, 0);
-  group_sum2_kernel<<<dim3((Cn + 31) / 32, 1), 256, 0, st>>>(scratch, out, 1, slabs, Cn, slabs, accumulate);
+  launch_group_sum2(src, scratch, slabs, 64, Cn, M, 0, st);
+  launch_group_sum2(scratch, out, 1, slabs, Cn, slabs, accumulate, st);
   return op_check("colsum kernels");
 }
 
