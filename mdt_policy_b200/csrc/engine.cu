@@ -80,6 +80,8 @@ struct Work {
   __nv_bfloat16 *a16, *y16, *h16;
   // algebraic cross-attention (cross_row_kernel): head-major key / value operands and the G / U / c tables of layer 0
   __nv_bfloat16 *ka16, *va16; float *gtab, *utab, *ctab;
+  // split-K workspace of the mlp c_proj GEMM (K = 4d): fp32 partial tiles + self-resetting per-tile counters, per sub-batch chain
+  float* sk_ws; unsigned* sk_cnt;
 };
 
 struct MdtHandle {
@@ -104,6 +106,8 @@ struct MdtHandle {
   int mod_rows = 0;
   // algebraic cross-attention tables (see cross_row_kernel); per-layer strides in elements
   bool cross_fused = false;
+  static constexpr int SK_MAX_SPLITS = 4;
+  float* sk_ws = nullptr; unsigned* sk_cnt = nullptr; int cproj_splits = 1;    // MDTB200_CPROJ_SPLITS
   __nv_bfloat16 *ka16 = nullptr, *va16 = nullptr; float *gtab = nullptr, *utab = nullptr, *ctab = nullptr;
   size_t cross_rows = 0, ka_layer_stride = 0, tab_layer_stride = 0, ctab_layer_stride = 0;
 
@@ -122,7 +126,7 @@ struct MdtHandle {
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES] = {};
   int branches = 4;               // MDTB200_BRANCHES overrides
 
-  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16, ka16, va16, gtab, utab, ctab}; }
+  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16, ka16, va16, gtab, utab, ctab, sk_ws, sk_cnt}; }
   // view of samples [b0, ...): every buffer is row-indexed by sample (encoder rows reuse the decoder row offsets, Tc <= T);
   // mc_off = padded context rows of the sub-batches before this one (each sub-batch owns a 128-row aligned block per head)
   Work slice(const Work& w, int b0, int mc_off = 0) const {
@@ -133,6 +137,10 @@ struct MdtHandle {
     o.xe += r * dd; o.ctx += (size_t)b0 * Tc * dd; o.kv += (size_t)b0 * Tc * Ld * 2 * dd;
     o.xh += r * dd; o.a += r * dd; o.qkv += r * 3 * dd; o.y += r * dd; o.hbuf += r * 4 * dd; o.q += r * dd;
     if (o.a16) { o.a16 += r * 2 * dd; o.y16 += r * 2 * dd; o.h16 += r * 8 * dd; }
+    if (o.sk_ws) {      // disjoint m-tile ranges per chain: floor(r / 128) + floor(b0 / 32) (chains have >= 32 samples)
+      const size_t t0 = r / 128 + (size_t)b0 / 32;
+      o.sk_ws += t0 * SK_MAX_SPLITS * 128 * dd; o.sk_cnt += t0 * (dd / 64);
+    }
     if (o.gtab) {
       const size_t hr = (size_t)H * mc_off;
       o.ka16 += hr * 128; o.va16 += hr * 128; o.gtab += hr * dd; o.utab += hr * dd; o.ctab += (size_t)b0 * H * Tc;
@@ -190,6 +198,7 @@ struct Gemm {
   int M = 0, N = 0, K = 0; int epi = EPI_NONE;
   int gi = 0, go = 0, goff = 0;
   int wg_rows = 0, wg_stride = 0, w_rows = 0;          // weight groups (tensor-core path only)
+  int splits = 1; float* sk_ws = nullptr; unsigned* sk_cnt = nullptr;     // deterministic split-K (tensor-core path only)
 };
 
 int launch_sgemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
@@ -232,6 +241,7 @@ int gemm(MdtHandle* h, const Gemm& p, cudaStream_t st) {
     t.passes = h->cfg.precision == MDTB200_PREC_BF16X3 ? 3 : 1;
     t.trace = nullptr; t.gi = p.gi; t.go = p.go; t.goff = p.goff;
     t.wg_rows = p.wg_rows; t.wg_stride = p.wg_stride; t.w_rows = p.w_rows;
+    if (p.splits > 1 && p.sk_ws && t.passes == 3) { t.splits = p.splits; t.sk_ws = p.sk_ws; t.sk_cnt = p.sk_cnt; }
     const char* e = tc::launch_tc_gemm(h->tma, t, st);
     if (e) return fail(h, MDTB200_ECUDA, "tcgen05 gemm (M=%d N=%d K=%d): %s", p.M, p.N, p.K, e);
     count_launch(h);
@@ -515,6 +525,7 @@ int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mo
     Gemm p;
     p.A = k.hbuf; p.lda = 4 * d; p.A16 = k.h16; p.lda16 = 8 * d; p.W = L.wproj; p.W16 = L.wproj16; p.bias = L.bproj; p.C = k.xh; p.ldc = d; p.R = k.xh; p.ldr = d;
     p.gate = ml + 5 * d; p.gate_stride = mod_stride; p.rows_per_group = T; p.M = M; p.N = d; p.K = 4 * d; p.epi = EPI_RES_GATE;
+    p.splits = h->cproj_splits; p.sk_ws = k.sk_ws; p.sk_cnt = k.sk_cnt;
     TRY(gemm(h, p, st));
   }
   head.xh = k.xh; head.lnw = w.dec_ln_w; head.lnb = w.dec_ln_b; head.W = w.ap_w; head.bias = w.ap_b;
@@ -1107,6 +1118,16 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   }
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { fail(h, MDTB200_ECUDA, "event creation failed"); return bail(MDTB200_ECUDA); }
   if (const char* e = getenv("MDTB200_BRANCHES")) h->branches = atoi(e);
+  if (cfg->precision == MDTB200_PREC_BF16X3) {
+    if (const char* e = getenv("MDTB200_CPROJ_SPLITS")) h->cproj_splits = atoi(e);
+    if (h->cproj_splits < 1 || h->cproj_splits > MdtHandle::SK_MAX_SPLITS) h->cproj_splits = 1;
+    if (h->cproj_splits > 1) {
+      const size_t tiles = ((size_t)cfg->max_batch * h->T + 127) / 128 + (size_t)cfg->max_batch / 32 + 2;
+      int rc2 = 0;
+      if ((rc2 = dev_alloc(h, &h->sk_ws, tiles * MdtHandle::SK_MAX_SPLITS * 128 * h->d)) || (rc2 = dev_alloc(h, &h->sk_cnt, tiles * (h->d / 64)))) return bail(rc2);
+      cudaMemset(h->sk_cnt, 0, tiles * (h->d / 64) * sizeof(unsigned));
+    }
+  }
   *out = h;
   return 0;
 }

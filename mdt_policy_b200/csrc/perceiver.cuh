@@ -190,7 +190,7 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
 // straight into the A fragments (each xhat element is used by exactly one warp) as 16-byte loads: within a 16-column chunk lane t
 // owns columns 4t..4t+3, which are the k indices (t, t+4) of two consecutive k-steps -- the same permutation is applied to B.
 struct ScoreArgs { const float* qt; const float* cq; const float* xhat; float* scores; int B, F, Fp, Q, H, Mp, d; };
-constexpr int SC_FPC = 64, SC_THREADS = 128;
+constexpr int SC_FPC = 128, SC_THREADS = 256;       // 8 warps share one copy of the query planes (2 CTAs = 16 warps per SM)
 inline int attn_nt(int HQ) { const int n = (HQ + 7) / 8; return n <= 4 ? n : n <= 6 ? 6 : 8; }     // instantiated n-tile counts: 1 2 3 4 6 8
 inline int score_dp(int d) { return d + 16; }                         // row stride = 16 (mod 32) words: conflict-free LDS.128 fragments
 inline size_t score_smem_bytes(int HQ, int d) { return (size_t)2 * attn_nt(HQ) * 8 * score_dp(d) * sizeof(float); }

@@ -256,7 +256,7 @@ class FinalNorm(Function):
 
 
 class NarrowIn(Function):
-    """y = x W^T + b for a few input features (action_emb: 7 -> d); x does not need a gradient"""
+    """y = x W^T + b for a few input features (action_emb: 7 -> d)"""
 
     @staticmethod
     def forward(ctx, x, w, b):
@@ -264,17 +264,24 @@ class NarrowIn(Function):
         x2 = T._c(x).reshape(-1, K)
         y = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
         T._gemm(0, x2, w, b, y, x2.shape[0], N, K)
-        ctx.save_for_backward(x2)
-        ctx.has_bias = b is not None
+        ctx.save_for_backward(x2, w)
+        ctx.cfg = (x.shape, b is not None)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
-        (x2,) = ctx.saved_tensors
-        dy2 = T._c(dy).reshape(x2.shape[0], -1)
+        x2, w = ctx.saved_tensors
+        xshape, has_bias = ctx.cfg
+        M, N, K = x2.shape[0], w.shape[0], w.shape[1]
+        dy2 = T._c(dy).reshape(M, N)
+        dx = None
+        if ctx.needs_input_grad[0]:          # only when the noised actions themselves carry a gradient (guidance-style uses)
+            dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+            T._gemm(1, dy2, w, None, dx, M, N, K)
+            dx = dx.view(xshape)
         dw = O.narrow_wgrad(dy2, x2, True)
-        db = T._colsum(dy2) if ctx.has_bias else None
-        return None, dw, db
+        db = T._colsum(dy2) if has_bias else None
+        return dx, dw, db
 
 
 class NarrowOut(Function):

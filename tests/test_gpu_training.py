@@ -150,6 +150,26 @@ def test_loss_and_all_gradients_vs_oracle_autograd(variant):
     print("worst gradient error / tolerance:", worst)
 
 
+def test_input_gradients_vs_oracle_autograd():
+    """d loss / d (noised actions via the action tensor, goal, state tokens): the fused training graph also carries gradients to its
+    inputs (guidance-style uses), checked against autograd over the oracle"""
+    cfg, ocfg, Bn = _no_dropout(H.mdtv_inner_cfg(2, 2)), orc.OracleCfg(n_enc_layers=2, n_dec_layers=2), 8
+    inp = synthetic_inputs(Bn, seed=94)
+    model = H.build_product(cfg, 91, "trained").train()
+    P = H.oracle_params([(n, p.shape) for n, p in model.named_parameters()], 91, "trained")
+    sigma = torch.exp(torch.linspace(2.0, -3.0, Bn))
+    xin = (inp["actions"] + inp["noise"] * sigma[:, None, None])
+    a_o, g_o, s_o = (t.clone().requires_grad_() for t in (xin, inp["goal"], inp["state_images"]))
+    out_o = orc.denoiser_forward(P, ocfg, {"state_images": s_o, "modality": "lang"}, a_o, g_o, sigma)
+    out_o.square().sum().backward()
+    a_c, g_c, s_c = (t.clone().cuda().requires_grad_() for t in (xin, inp["goal"], inp["state_images"]))
+    out = model({"state_images": s_c, "modality": "lang"}, a_c, g_c, sigma.cuda())
+    out.square().sum().backward()
+    for name, got, want in (("actions", a_c.grad, a_o.grad), ("goal", g_c.grad, g_o.grad), ("state", s_c.grad, s_o.grad)):
+        assert got is not None, name
+        assert float((got.cpu() - want).abs().max()) < 1e-3 * float(want.abs().max()) + 1e-6, name
+
+
 def test_gradients_vs_reference_fingerprints():
     """The same check against the reference itself: fingerprints (L2 norm + 8 probe entries per parameter) of the gradients
     of the reference's GCDenoiser.loss, generated by tests/golden/make_golden.py."""
