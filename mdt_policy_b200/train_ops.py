@@ -70,6 +70,8 @@ class SplitKWorkspace:
         if inst.ws.numel() < floats:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("split-K workspace must be sized before CUDA-graph capture (run one eager step first)")
+            if slot == 1 and inst.ws.numel() > 0:
+                inst.ws.record_stream(_side(device))      # kernels on the side stream may still be using the old buffer
             inst.ws = torch.empty(int(floats * 1.25), dtype=torch.float32, device=device)
         return inst
 
