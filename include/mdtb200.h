@@ -63,7 +63,8 @@ enum { MDTB200_VARIANT_MDTV = 0, MDTB200_VARIANT_MDT = 1 };
 enum { MDTB200_PREC_FP32 = 0, MDTB200_PREC_BF16X3 = 1, MDTB200_PREC_BF16 = 2 };
 
 /* fused samplers (gc_sampling.py) */
-enum { MDTB200_SAMPLER_DDIM = 0, MDTB200_SAMPLER_EULER = 1, MDTB200_SAMPLER_HEUN = 2, MDTB200_SAMPLER_DPMPP_2M = 3 };
+enum { MDTB200_SAMPLER_DDIM = 0, MDTB200_SAMPLER_EULER = 1, MDTB200_SAMPLER_HEUN = 2, MDTB200_SAMPLER_DPMPP_2M = 3,
+       MDTB200_SAMPLER_EULER_ANCESTRAL = 4 /* only through mdtb200_sample_ancestral (needs the caller's noise) */ };
 
 /* goal modality: selects lang_emb vs goal_emb (mdtv_transformer.py:268-273) */
 enum { MDTB200_MODALITY_VIS = 0, MDTB200_MODALITY_LANG = 1 };
@@ -135,6 +136,12 @@ MDTB200_API int mdtb200_sample(MdtHandle* h, int sampler, const float* sigmas, i
 MDTB200_API int mdtb200_sample_host(MdtHandle* h, int sampler, const float* sigmas_host, int n_steps,
                         const float* goal_host, const float* state_host, int modality, int B,
                         float* x_inout_host, void* stream);
+
+/* sample_euler_ancestral (gc_sampling.py:213-253) as one CUDA graph.  The sampler is stochastic: `noise` holds the standard-normal
+ * draws of every step, (n_steps, B, T_a, action_dim) on the device, produced by the CALLER in the reference's order (one
+ * torch.randn_like per step whose sigma_down > 0, zeros elsewhere) so that the RNG stream is the reference's; eta as in the reference. */
+MDTB200_API int mdtb200_sample_ancestral(MdtHandle* h, const float* sigmas, int n_steps, const float* goal, const float* state, int modality,
+                                         int B, float* x_inout, const float* noise, float eta, void* stream);
 
 /* introspection ---------------------------------------------------------------------------- */
 /* number of kernels this handle has launched (graph replays count their kernel nodes) */

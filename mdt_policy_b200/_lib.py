@@ -13,13 +13,13 @@ ABI_VERSION = 1
 # enums of include/mdtb200.h
 VARIANT = {"mdtv": 0, "mdt": 1}
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
-SAMPLER = {"ddim": 0, "euler": 1, "heun": 2, "dpmpp_2m": 3}
+SAMPLER = {"ddim": 0, "euler": 1, "heun": 2, "dpmpp_2m": 3, "euler_ancestral": 4}
 MODALITY_VIS, MODALITY_LANG = 0, 1
 
 EXPORTS = [
     "mdtb200_abi_version", "mdtb200_create", "mdtb200_destroy", "mdtb200_last_error",
     "mdtb200_bind_weight", "mdtb200_commit_weights", "mdtb200_encode", "mdtb200_set_context",
-    "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_launch_count",
+    "mdtb200_denoise", "mdtb200_sample", "mdtb200_sample_host", "mdtb200_sample_ancestral", "mdtb200_launch_count",
     "mdtb200_debug_copy", "mdtb200_debug_gemm", "mdtb200_debug_gemm_time", "mdtb200_debug_ktrace",
     "mdtb200_op_gemm", "mdtb200_op_gemm_tc", "mdtb200_op_gemm_tc_scratch", "mdtb200_op_group_sum", "mdtb200_op_colsum", "mdtb200_op_act", "mdtb200_op_ln_fwd", "mdtb200_op_ln_bwd",
     "mdtb200_op_attn_fwd", "mdtb200_op_attn_bwd", "mdtb200_op_gate_res", "mdtb200_op_gate_res_bwd", "mdtb200_op_dropout", "mdtb200_op_adamw_ema", "mdtb200_op_set_seed_epoch",
@@ -72,6 +72,8 @@ def _declare(lib):
     lib.mdtb200_sample.restype = i32
     lib.mdtb200_sample_host.argtypes = [vp, i32, fp, i32, fp, fp, i32, i32, fp, vp]
     lib.mdtb200_sample_host.restype = i32
+    lib.mdtb200_sample_ancestral.argtypes = [vp, fp, i32, fp, fp, i32, i32, fp, fp, C.c_float, vp]
+    lib.mdtb200_sample_ancestral.restype = i32
     lib.mdtb200_launch_count.argtypes = [vp]
     lib.mdtb200_launch_count.restype = i64
     lib.mdtb200_debug_copy.argtypes = [vp, C.c_char_p, fp, i64, vp]

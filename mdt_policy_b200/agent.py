@@ -119,7 +119,7 @@ class DenoiseAgent:
         of the actions, one synchronisation.  This is the call bench.py's ``e2e`` number times."""
         dev = self.device
         inner = getattr(self.model, "inner_model", None)
-        fused = self.sampler_type in ("ddim", "euler", "heun", "dpmpp_2m") and getattr(inner, "_variant", None) == "mdtv"
+        fused = self.sampler_type in ("ddim", "euler", "heun", "dpmpp_2m") and getattr(inner, "_variant", None) == "mdtv"     # (ancestral: device path)
         host_ok = all((not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous()
                       for t in (state_images_host, latent_goal_host, x_T_host))     # raw float* through the C ABI: no silent casts
         if fused and host_ok:

@@ -82,6 +82,7 @@ struct Work {
   __nv_bfloat16 *ka16, *va16; float *gtab, *utab, *ctab;
   // split-K workspace of the mlp c_proj GEMM (K = 4d): fp32 partial tiles + self-resetting per-tile counters, per sub-batch chain
   float* sk_ws; unsigned* sk_cnt;
+  float* noise;           // ancestral sampler: per-step noise rows of this (sub-)batch, step stride = MdtHandle::noise_stride
 };
 
 struct MdtHandle {
@@ -106,6 +107,7 @@ struct MdtHandle {
   int mod_rows = 0;
   // algebraic cross-attention tables (see cross_row_kernel); per-layer strides in elements
   bool cross_fused = false;
+  float* noise = nullptr; size_t noise_stride = 0; float* anc_eta = nullptr;     // fused euler_ancestral: static noise buffer (lazily allocated)
   static constexpr int SK_MAX_SPLITS = 4;
   float* sk_ws = nullptr; unsigned* sk_cnt = nullptr; int cproj_splits = 1;    // MDTB200_CPROJ_SPLITS
   __nv_bfloat16 *ka16 = nullptr, *va16 = nullptr; float *gtab = nullptr, *utab = nullptr, *ctab = nullptr;
@@ -126,7 +128,7 @@ struct MdtHandle {
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES] = {};
   int branches = 4;               // MDTB200_BRANCHES overrides
 
-  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16, ka16, va16, gtab, utab, ctab, sk_ws, sk_cnt}; }
+  Work work() const { return Work{in_goal, in_state, x, x2, dbuf, gh, xe, ctx, kv, xh, a, qkv, y, hbuf, q, a16, y16, h16, ka16, va16, gtab, utab, ctab, sk_ws, sk_cnt, noise}; }
   // view of samples [b0, ...): every buffer is row-indexed by sample (encoder rows reuse the decoder row offsets, Tc <= T);
   // mc_off = padded context rows of the sub-batches before this one (each sub-batch owns a 128-row aligned block per head)
   Work slice(const Work& w, int b0, int mc_off = 0) const {
@@ -134,6 +136,7 @@ struct MdtHandle {
     Work o = w;
     o.in_goal += (size_t)b0 * cfg.goal_dim; o.in_state += (size_t)b0 * Ts * cfg.obs_dim;
     o.x += r * A; o.x2 += r * A; o.dbuf += r * A; o.gh += (size_t)b0 * 2 * dd;
+    if (o.noise) o.noise += r * A;
     o.xe += r * dd; o.ctx += (size_t)b0 * Tc * dd; o.kv += (size_t)b0 * Tc * Ld * 2 * dd;
     o.xh += r * dd; o.a += r * dd; o.qkv += r * 3 * dd; o.y += r * dd; o.hbuf += r * 4 * dd; o.q += r * dd;
     if (o.a16) { o.a16 += r * 2 * dd; o.y16 += r * 2 * dd; o.h16 += r * 8 * dd; }
@@ -545,6 +548,7 @@ int sample_steps(MdtHandle* h, const Work& k, int sampler, int n_steps, int moda
       case MDTB200_SAMPLER_EULER: hd.mode = HEAD_EULER; break;
       case MDTB200_SAMPLER_HEUN: hd.mode = HEAD_HEUN1; break;
       case MDTB200_SAMPLER_DPMPP_2M: hd.mode = HEAD_DPMPP2M; break;
+      case MDTB200_SAMPLER_EULER_ANCESTRAL: hd.mode = HEAD_EULER_ANC; hd.noise = k.noise + (size_t)i * h->noise_stride; hd.eta = h->anc_eta; break;
       default: return fail(h, MDTB200_EINVAL, "unknown sampler %d", sampler);
     }
     TRY(decoder_eval(h, k, k.x, h->mod + i * mrow, 0, h->sigmas + i, 0, 1, B, hd, st));
@@ -1236,7 +1240,7 @@ static int get_graph(MdtHandle* h, int sampler, int n_steps, int modality, int B
   }
   GraphEntry ge{};
   h->capture_count = 0;
-  if (h->fused) TRY(build_fused_plan(h, B, sampler_evals(h, sampler, n_steps), n_steps, h->mod, 0, h->sigmas, 0, 1, nullptr, &ge.plan));
+  if (h->fused && sampler != MDTB200_SAMPLER_EULER_ANCESTRAL) TRY(build_fused_plan(h, B, sampler_evals(h, sampler, n_steps), n_steps, h->mod, 0, h->sigmas, 0, 1, nullptr, &ge.plan));
   static const bool split = !getenv("MDTB200_SINGLE_GRAPH");
   const int s0 = (!ge.plan && split && n_steps > 3) ? 2 : n_steps;
   h->cur_plan = ge.plan;
@@ -1258,7 +1262,7 @@ static int check_sample_args(MdtHandle* h, int sampler, int n_steps, int B, cons
   TRY(check_ready(h, B));
   if (!a || !b || !c || !d) return fail(h, MDTB200_EINVAL, "sample: null argument");
   if (n_steps < 1 || n_steps > MAX_STEPS) return fail(h, MDTB200_EINVAL, "n_steps %d outside [1, %d]", n_steps, MAX_STEPS);
-  if (sampler < MDTB200_SAMPLER_DDIM || sampler > MDTB200_SAMPLER_DPMPP_2M) return fail(h, MDTB200_EINVAL, "unknown sampler %d", sampler);
+  if (sampler < MDTB200_SAMPLER_DDIM || sampler > MDTB200_SAMPLER_EULER_ANCESTRAL) return fail(h, MDTB200_EINVAL, "unknown sampler %d", sampler);
   return 0;
 }
 
@@ -1280,15 +1284,34 @@ static int sample_impl(MdtHandle* h, int sampler, const float* sigmas, int n_ste
   return 0;
 }
 
+MDTB200_API int mdtb200_sample_ancestral(MdtHandle* h, const float* sigmas, int n_steps, const float* goal, const float* state, int modality,
+                                         int B, float* x_inout, const float* noise, float eta, void* stream) {
+  if (!h) return MDTB200_EINVAL;
+  TRY(check_sample_args(h, MDTB200_SAMPLER_EULER_ANCESTRAL, n_steps, B, sigmas, goal, state, x_inout));
+  if (!noise) return fail(h, MDTB200_EINVAL, "sample_ancestral: null noise");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->noise) {      // static (graph-visible) noise buffer: MAX_STEPS rows of max_batch * T * A draws, and the eta scalar
+    h->noise_stride = (size_t)h->cfg.max_batch * h->T * h->A;
+    int rc = 0;
+    if ((rc = dev_alloc(h, &h->noise, (size_t)MAX_STEPS * h->noise_stride)) || (rc = dev_alloc(h, &h->anc_eta, 4))) return rc;
+  }
+  const size_t row = (size_t)B * h->T * h->A * 4;
+  CUDA_TRY(h, cudaMemcpy2DAsync(h->noise, h->noise_stride * 4, noise, row, row, n_steps, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->anc_eta, &eta, 4, cudaMemcpyHostToDevice, st));      // 4 bytes from the stack: staged by the driver before return
+  return sample_impl(h, MDTB200_SAMPLER_EULER_ANCESTRAL, sigmas, n_steps, goal, state, modality, B, x_inout, st, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+}
+
 MDTB200_API int mdtb200_sample(MdtHandle* h, int sampler, const float* sigmas, int n_steps, const float* goal, const float* state, int modality, int B,
                    float* x_inout, void* stream) {
   if (!h) return MDTB200_EINVAL;
+  if (sampler == MDTB200_SAMPLER_EULER_ANCESTRAL) return fail(h, MDTB200_EINVAL, "the ancestral sampler needs the caller's noise: use mdtb200_sample_ancestral");
   return sample_impl(h, sampler, sigmas, n_steps, goal, state, modality, B, x_inout, (cudaStream_t)stream, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
 }
 
 MDTB200_API int mdtb200_sample_host(MdtHandle* h, int sampler, const float* sigmas_host, int n_steps, const float* goal_host, const float* state_host, int modality,
                         int B, float* x_inout_host, void* stream) {
   if (!h) return MDTB200_EINVAL;
+  if (sampler == MDTB200_SAMPLER_EULER_ANCESTRAL) return fail(h, MDTB200_EINVAL, "the ancestral sampler needs the caller's noise: use mdtb200_sample_ancestral");
   cudaStream_t st = (cudaStream_t)stream;
   TRY(sample_impl(h, sampler, sigmas_host, n_steps, goal_host, state_host, modality, B, x_inout_host, st, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaStreamSynchronize(st));

@@ -818,7 +818,8 @@ enum HeadMode : int {
   HEAD_EULER = 3,      // x <- x + (x - D)/s * (s' - s)
   HEAD_HEUN1 = 4,      // d = (x - D)/s ; dbuf = d ; x2 = x + d dt   (x kept)
   HEAD_HEUN2 = 5,      // d2 = (x2 - D2)/s' ; x <- x + (dbuf + d2)/2 dt
-  HEAD_DPMPP2M = 6     // multistep with old denoised in dbuf
+  HEAD_DPMPP2M = 6,    // multistep with old denoised in dbuf
+  HEAD_EULER_ANC = 7   // x <- x + (x - D)/s (s_down - s) + noise s_up     (sample_euler_ancestral, gc_sampling.py:213-253)
 };
 struct HeadArgs {
   const float* xh; const float* lnw; const float* lnb; const float* W; const float* bias;  // W (A, d)
@@ -830,6 +831,7 @@ struct HeadArgs {
   const float* sigma; int sigma_stride;   // per-sample sigma (RAW/DENOISE); sampler modes use sigmas[step]
   const float* sigmas; int step; int n_steps;
   int M, d, A, T, mode; float sigma_data;
+  const float* noise; const float* eta;   // EULER_ANC: this step's standard-normal draws (M x A, drawn by the caller: torch's RNG stream) and eta (device scalar)
 };
 
 template <int VPL>
@@ -917,6 +919,18 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
         float d2 = (xin - D) / sig;
         float dp = (a.dbuf[e] + d2) / 2.0f;
         a.x_state[e] = a.x_state[e] + dp * dt;
+      } break;
+      case HEAD_EULER_ANC: {   // get_ancestral_step (gc_sampling.py:102-109) in torch's fp32 op order, then the Euler step to sigma_down
+        const float eta = *a.eta;
+        float s_down = sig_next, s_up = 0.f;
+        if (eta != 0.f) {
+          s_up = fminf(sig_next, eta * sqrtf(sig_next * sig_next * (sig * sig - sig_next * sig_next) / (sig * sig)));
+          s_down = sqrtf(sig_next * sig_next - s_up * s_up);
+        }
+        float dd = (xin - D) / sig;
+        float xn = xin + dd * (s_down - sig);
+        if (s_down > 0.f) xn = xn + a.noise[e] * s_up;
+        a.x_state[e] = xn;
       } break;
       case HEAD_DPMPP2M: {
         float t = -logf(sig), tn = -logf(sig_next), h = tn - t;

@@ -109,7 +109,7 @@ def _on_cuda(*tensors) -> bool:
 
 # --------------------------------------------------------------------------------------------------- samplers
 # Every sampler below first tries the fused CUDA path (GCDenoiser.sample -> mdtb200_sample: the whole loop is one CUDA graph).
-# Anything the graph does not cover (callbacks, scalers, churn, extra_args, the stochastic ancestral sampler, foreign models)
+# Anything the graph does not cover (callbacks, scalers, churn, extra_args, foreign models)
 # runs through ONE generic driver, `_integrate`, parameterised by a per-sampler update rule; the rules are the formulas of
 # mdt/models/edm_diffusion/gc_sampling.py (cited per rule), the signatures and callback payloads are the reference's.
 
@@ -212,7 +212,17 @@ def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None
 @torch.no_grad()
 def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
                            disable=None, eta=1.):
-    """gc_sampling.py:213-253 (stochastic: the noise of every step comes from torch's generator, as in the reference)."""
+    """gc_sampling.py:213-253 (stochastic: the noise of every step comes from torch's generator, as in the reference).
+    Fused path: the draws are made up front in the reference's order (one randn_like per step whose sigma_down > 0) and the whole
+    loop runs as one CUDA graph (mdtb200_sample_ancestral); the generic driver covers callbacks / scalers / foreign models."""
+    if _fused_ok(model, scaler, extra_args or {}, callback) and _on_cuda(action, goal):
+        sig = sigmas.detach().float().cpu()
+        n = sig.numel() - 1
+        noise = torch.zeros((n,) + tuple(action.shape), dtype=torch.float32, device=action.device)
+        for i in range(n):
+            if get_ancestral_step(sig[i], sig[i + 1], eta=eta)[0] > 0:
+                noise[i] = torch.randn_like(action)
+        return model.sample(state, action, goal, sigmas, sampler="euler_ancestral", noise=noise, eta=eta)
     return _integrate(_rule_euler_ancestral, model, state, action, goal, sigmas, scaler, extra_args, callback, eta=eta)
 
 

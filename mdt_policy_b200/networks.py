@@ -381,7 +381,9 @@ class _ScoreNetBase(nn.Module):
         return self._decode(eng, actions, sigma, False)
 
     # fused sampling (MDTVAgent.sample_loop for ddim / euler / heun / dpmpp_2m)
-    def sample(self, states, x_t, goals, sigmas, sampler: str = "ddim", uncond: bool = False):
+    def sample(self, states, x_t, goals, sigmas, sampler: str = "ddim", uncond: bool = False, noise=None, eta: float = 1.0):
+        """noise / eta: euler_ancestral only -- noise (n_steps, B, T, A) holds the standard-normal draw of every step (zeros where the
+        reference draws nothing), produced by the caller so that the RNG stream is the reference's (gc_sampling.sample_euler_ancestral)."""
         self._check_mode()
         state = self._prep_state(states)
         goal = self._prep_goal(goals, self._states_length(states), bool(uncond))
@@ -390,6 +392,14 @@ class _ScoreNetBase(nn.Module):
         x = _f32c(x_t, "x_t").clone()
         sig = _f32c(sigmas, "sigmas").to(state.device)
         n_steps = sig.numel() - 1
+        if sampler == "euler_ancestral":
+            if noise is None or tuple(noise.shape) != (n_steps,) + tuple(x.shape):
+                raise ValueError("euler_ancestral needs noise of shape (n_steps, B, T, A)")
+            noise = _f32c(noise, "noise")
+            with torch.cuda.device(eng.device):
+                eng.check(eng.lib.mdtb200_sample_ancestral(eng.handle, _ptr(sig), n_steps, _ptr(goal), _ptr(state), self._modality(states, False), B,
+                                                           _ptr(x), _ptr(noise), float(eta), eng.stream), "mdtb200_sample_ancestral")
+            return x
         with torch.cuda.device(eng.device):
             eng.check(eng.lib.mdtb200_sample(eng.handle, _lib.SAMPLER[sampler], _ptr(sig), n_steps, _ptr(goal), _ptr(state),
                                              self._modality(states, False), B, _ptr(x), eng.stream), "mdtb200_sample")

@@ -188,7 +188,7 @@ def test_weights_resync_after_update():
 
 def test_agent_host_path_uncond_and_ancestral():
     """DenoiseAgent end-to-end on HOST tensors (the e2e path bench.py times) vs the oracle; classifier-free `uncond`
-    (goal zeroed, mdtv_transformer.py:256-257); the stochastic euler_ancestral sampler runs through the generic loop."""
+    (goal zeroed, mdtv_transformer.py:256-257); the stochastic euler_ancestral sampler as a fused graph vs the generic loop."""
     from mdt_policy_b200 import DenoiseAgent, gc_sampling as gcs
     model = H.build_product(H.mdtv_inner_cfg(2, 2, precision="bf16x3"), 81, "trained")
     P = H.oracle_params([(n, p.shape) for n, p in model.named_parameters()], 81, "trained")
@@ -215,12 +215,20 @@ def test_agent_host_path_uncond_and_ancestral():
                                  torch.zeros_like(inp["goal"]), s1.cpu())
     assert torch.equal(a, b)
     assert (a.cpu() - w).abs().max() < 1e-4 * max(1.0, float(w.abs().max()))
-    # stochastic sampler: generic loop, finite output, reproducible under a fixed torch seed
-    torch.manual_seed(0)
-    e1 = gcs.sample_euler_ancestral(model, state, inp["x_T"].cuda(), inp["goal"].cuda(), sig.cuda())
-    torch.manual_seed(0)
-    e2 = gcs.sample_euler_ancestral(model, state, inp["x_T"].cuda(), inp["goal"].cuda(), sig.cuda())
-    assert torch.isfinite(e1).all() and torch.equal(e1, e2)
+    # stochastic sampler: the fused graph (noise drawn up front in the reference's order) is reproducible under a fixed torch seed and
+    # agrees with the generic per-step driver on the same RNG stream, for eta = 1, 0.5 and 0 (which still consumes one draw per step)
+    for eta in (1.0, 0.5, 0.0):
+        torch.manual_seed(0)
+        e1 = gcs.sample_euler_ancestral(model, state, inp["x_T"].cuda(), inp["goal"].cuda(), sig.cuda(), eta=eta)
+        after_fused = torch.rand(3, device="cuda")
+        torch.manual_seed(0)
+        e2 = gcs.sample_euler_ancestral(model, state, inp["x_T"].cuda(), inp["goal"].cuda(), sig.cuda(), eta=eta)
+        assert torch.isfinite(e1).all() and torch.equal(e1, e2)
+        torch.manual_seed(0)
+        e3 = gcs._integrate(gcs._rule_euler_ancestral, model, state, inp["x_T"].cuda(), inp["goal"].cuda(), sig.cuda(), None, None, None, eta=eta)
+        after_generic = torch.rand(3, device="cuda")
+        assert (e1 - e3).abs().max() < 1e-4 * max(1.0, float(e3.abs().max())), eta
+        assert torch.equal(after_fused, after_generic)            # both leave the generator in the same state
 
 
 @pytest.mark.parametrize("variant,B", [("mdtv", 200), ("mdtv", 131), ("mdt", 160)])

@@ -1,8 +1,1 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
-timeout 900 python -m pytest tests/test_perceiver.py -m gpu -x -q 2>&1 | tail -3
-python - <<'PY'
-import torch, sys
-sys.path.insert(0, ".")
-import bench
-print(bench.perceiver_measure(torch.device("cuda"), 256))
-PY
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cabi.py tests/test_r2_pins.py -m gpu -x -q 2>&1 | tail -4
