@@ -144,6 +144,9 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             if rc != 0:
                 raise RuntimeError(f"mdtb200_op_adamw_ema failed ({rc}): {self._lib.mdtb200_last_error(None).decode()}")
+            # the kernel writes the parameters through raw pointers: tell autograd / the inference engine's staleness check
+            # (networks._Engine.sync_weights keys on Parameter._version) that they changed
+            torch.autograd.graph.increment_version(params)
         return loss
 
 
@@ -157,7 +160,9 @@ class GraphedTrainStep:
     The eager step issues ~1500 small kernels from Python (two thirds of its wall time is host sequencing); the replayed graph
     issues them from the GPU front end.  Dropout masks stay fresh on every replay through a device-side RNG epoch counter that the
     graph increments (``mdtb200_op_set_seed_epoch``); the optimizer's step count lives on the device as well.  Shapes are fixed at
-    capture time (as for any CUDA graph); parameters without a gradient at capture time stay frozen.
+    capture time (as for any CUDA graph); parameters without a gradient at capture time stay frozen.  As with any torch.cuda.graph
+    capture of a backward pass, no autograd graph of an earlier eager step may still be alive (e.g. a kept `loss` tensor): its
+    AccumulateGrad nodes are bound to the default stream and the capture fails with cudaErrorStreamCaptureImplicit.
     """
 
     def __init__(self, model, optimizer: FusedAdamWEMA, state_images, goal, actions, noise, sigma, modality="lang", warmup=3,
@@ -173,6 +178,7 @@ class GraphedTrainStep:
         self.pg = process_group
         self.dp = (dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1) if data_parallel is None else bool(data_parallel)
         self.comm = True                  # set False to time the step without the all-reduce (exposed communication = difference)
+        self._bump = [p for group in optimizer.param_groups for p in group["params"]][:1]
         self.static = [t.detach().clone() for t in (state_images, goal, actions, noise, sigma)]
         lib = _lib.load()
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -181,6 +187,12 @@ class GraphedTrainStep:
         if self.dp:
             for p in model.parameters():
                 dist.broadcast(p.data, 0, group=process_group)
+        # The score network stashes its encoder output WITH its autograd graph (`latent_encoder_emb`, as the reference does for the
+        # CLA loss).  After eager steps on the default stream that graph keeps the encoder parameters' AccumulateGrad nodes alive and
+        # bound to the legacy stream, which a capturing stream may not synchronise with (cudaErrorStreamCaptureImplicit): drop it.
+        inner = getattr(model, "inner_model", None)
+        if inner is not None and getattr(inner, "latent_encoder_emb", None) is not None:
+            inner.latent_encoder_emb = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -191,6 +203,8 @@ class GraphedTrainStep:
                 self.opt.step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from . import train_ops
+        train_ops.presize_side_workspace(dev)      # the captured step runs its weight-gradient GEMMs on a side stream
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
         if not self.dp:
@@ -231,6 +245,7 @@ class GraphedTrainStep:
                 import torch.distributed as dist
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.pg)
             self.graph2.replay()
+        torch.autograd.graph.increment_version(self._bump)      # a replay updates the parameters without touching their version counters
         return self.loss
 
     def close(self):

@@ -140,6 +140,41 @@ def test_ddp_two_gpu_gradients_are_rank_means_and_weights_stay_in_sync():
         assert c0 == c1                        # identical weights on both ranks after the fused optimizer step
 
 
+def test_inference_engine_sees_fused_optimizer_and_graph_replay_updates():
+    """The fused optimizer kernel and a CUDA-graph replay write the parameters through raw pointers; the inference engine (weight arena
+    packed at first use) must still notice: eval loss (inference kernels) == train-path loss (dropout 0) after every kind of update."""
+    from mdt_policy_b200.optim import GraphedTrainStep
+    model = H.build_product(H.mdtv_inner_cfg(1, 1, attn_pdrop=0.0, resid_pdrop=0.0, mlp_pdrop=0.0), 95, "trained")
+    inp = {k: v.cuda() for k, v in synthetic_inputs(32, seed=96).items()}
+    sigma = torch.exp(torch.linspace(2.0, -3.0, 32)).cuda()
+    state = {"state_images": inp["state_images"], "modality": "lang"}
+    args = (inp["state_images"], inp["goal"], inp["actions"], inp["noise"], sigma)
+
+    def both():
+        model.eval()
+        with torch.no_grad():
+            l_inf = float(model.loss(state, inp["actions"], inp["goal"], inp["noise"], sigma)[0])     # inference engine
+        model.train()
+        l_tr = float(model.loss(state, inp["actions"], inp["goal"], inp["noise"], sigma)[0])          # training kernels, live parameters
+        return l_inf, l_tr
+
+    l0, t0 = both()                                   # packs the weight arena of the inference engine
+    assert abs(l0 - t0) < 1e-3 * max(1.0, t0)
+    opt = FusedAdamWEMA(model.parameters(), lr=1e-3, betas=(0.9, 0.9), weight_decay=0.05, ema_decay=0.99, capturable=True)
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        model.loss(state, inp["actions"], inp["goal"], inp["noise"], sigma)[0].backward()
+        opt.step()
+    l1, t1 = both()
+    assert t1 < t0 and abs(l1 - t1) < 1e-3 * max(1.0, t1), (l0, l1, t1)       # eager fused step: engine re-synced
+    step = GraphedTrainStep(model, opt, *args)
+    for _ in range(3):
+        step(*args)
+    l2, t2 = both()
+    step.close()
+    assert t2 < t1 and abs(l2 - t2) < 1e-3 * max(1.0, t2), (l1, l2, t2)       # graph replays: engine re-synced
+
+
 def _graphed_dp_worker(rank, world, port, ret):
     """data-parallel GraphedTrainStep: [fwd + bwd] graph | one NCCL all-reduce | [fused AdamW/EMA] graph, vs an eager loop that averages
     the two ranks' gradients by hand (dropout off so both are deterministic)"""
