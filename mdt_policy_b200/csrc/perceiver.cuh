@@ -282,11 +282,11 @@ struct ZArgs {
   const float* scores; const float* qkv; int ldq; int inner; const float* xhat;
   __nv_bfloat16* z16; float* wsum; float* olat; int B, F, Fp, Q, H, Mp, d;
 };
-constexpr int Z_CT = 128, Z_THREADS = 128;
+constexpr int Z_CT = 256, Z_THREADS = 256;
 inline int z_sp(int F, int Q) { return (F + Q + 3) / 8 * 8 + 4; }     // row stride = 4 (mod 8) words >= F + Q: conflict-free LDS.32 B fragments
 inline size_t z_smem_bytes(int HQ, int F, int Q) { return (size_t)2 * attn_nt(HQ) * 8 * z_sp(F, Q) * sizeof(float); }
 template <int NT>
-__global__ void __launch_bounds__(Z_THREADS) perceiver_softmax_z_kernel(ZArgs a) {
+__global__ void __launch_bounds__(Z_THREADS, 2) perceiver_softmax_z_kernel(ZArgs a) {
   extern __shared__ __align__(16) float z_smem[];
   pdl_enter();
   const int HQ = a.H * a.Q, NK = a.F + a.Q, SP = (NK + 3) / 8 * 8 + 4, d = a.d, NR = NT * 8;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(Z_THREADS) perceiver_softmax_z_kernel(ZArgs a)
   const uint32_t* bh = reinterpret_cast<const uint32_t*>(sa) + g * SP + t;
   const uint32_t* bl = sl + g * SP + t;
   const int nks = (a.F + 7) / 8;
-  constexpr int Z_PF = 7;                                    // register ring, as in the scores kernel
+  constexpr int Z_PF = 5;                                    // register ring, as in the scores kernel
   auto xrow = [&](int k) { return reinterpret_cast<const float4*>(xp + (size_t)(k < a.F ? k : a.F - 1) * d); };
   float4 r1[Z_PF], r2[Z_PF];
 #pragma unroll
