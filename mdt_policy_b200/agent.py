@@ -99,6 +99,20 @@ class DenoiseAgent:
             return gcs.sample_euler_ancestral(self.model, state, x_t, goal, sigmas, disable=True)
         if sampler_type == 'dpmpp_2m':
             return gcs.sample_dpmpp_2m(self.model, state, x_t, goal, sigmas, disable=True)
+        # the remaining working samplers of the reference (generic per-step driver; 'dpm_adaptive' / 'dpm_fast' are broken in the
+        # reference itself and 'dpmpp_2m_sde' needs torchsde: SURVEY 8 a5)
+        if sampler_type == 'lms':
+            return gcs.sample_lms(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'ancestral':
+            return gcs.sample_dpm_2_ancestral(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'dpm':
+            return gcs.sample_dpm_2(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'dpmpp_2s_ancestral':
+            return gcs.sample_dpmpp_2s_ancestral(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'dpmpp_2s':
+            return gcs.sample_dpmpp_2s(self.model, state, x_t, goal, sigmas, disable=True)
+        if sampler_type == 'dpmpp_2_with_lms':
+            return gcs.sample_dpmpp_2_with_lms(self.model, state, x_t, goal, sigmas, disable=True)
         raise ValueError('desired sampler type not found!')
 
     # mdtv_agent.py:523-550

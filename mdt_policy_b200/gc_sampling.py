@@ -153,12 +153,82 @@ def _rule_dpmpp_2m(ctx, x, denoised, sigma, sigma_next):                   # :71
     return _log_step(x, (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old_denoised, sigma, sigma_next)
 
 
-def _integrate(rule, model, state, x, goal, sigmas, scaler=None, extra_args=None, callback=None, cb_key="x", churn=None, eta=1.):
+def _rule_dpm_2(ctx, x, denoised, sigma, sigma_next):                      # :340-372: midpoint rule, midpoint taken in log sigma
+    d = to_d(x, sigma, denoised)
+    if sigma_next == 0:
+        return x + d * (sigma_next - sigma)
+    sigma_mid = sigma.log().lerp(sigma_next.log(), 0.5).exp()
+    x_mid = x + d * (sigma_mid - sigma)
+    return x + to_d(x_mid, sigma_mid, ctx["eval"](x_mid, sigma_mid)) * (sigma_next - sigma)
+
+
+def _rule_dpm_2_ancestral(ctx, x, denoised, sigma, sigma_next):            # :389-408
+    sigma_down, sigma_up = get_ancestral_step(sigma, sigma_next, eta=ctx["eta"])
+    if sigma_down == 0:
+        return x + to_d(x, sigma, denoised) * (sigma_down - sigma)
+    x = _rule_dpm_2(ctx, x, denoised, sigma, sigma_down)
+    return x + torch.randn_like(x) * sigma_up
+
+
+def _two_stage_log_step(ctx, x, denoised, sigma, sigma_to):
+    """DPM-Solver++(2S) step from sigma to sigma_to (:983-990 / :906-913): half step in t = -log sigma, re-evaluation there, full step
+    with the midpoint prediction"""
+    t, t_to = -sigma.log(), -sigma_to.log()
+    h = t_to - t
+    s = t + 0.5 * h
+    x_2 = ((-s).exp() / (-t).exp()) * x - torch.expm1(-h * 0.5) * denoised
+    denoised_2 = ctx["eval"](x_2, (-s).exp())
+    return ((-t_to).exp() / (-t).exp()) * x - torch.expm1(-h) * denoised_2
+
+
+def _rule_dpmpp_2s(ctx, x, denoised, sigma, sigma_next):                   # :975-992
+    if sigma_next == 0:
+        return x + to_d(x, sigma, denoised) * (sigma_next - sigma)
+    return _two_stage_log_step(ctx, x, denoised, sigma, sigma_next)
+
+
+def _rule_dpmpp_2s_ancestral(ctx, x, denoised, sigma, sigma_next):         # :895-917 (the noise term is evaluated on every step)
+    sigma_down, sigma_up = get_ancestral_step(sigma, sigma_next, eta=ctx["eta"])
+    if sigma_down == 0:
+        x = x + to_d(x, sigma, denoised) * (sigma_down - sigma)
+    else:
+        x = _two_stage_log_step(ctx, x, denoised, sigma, sigma_down)
+    return x + ctx["noise_sampler"](sigma, sigma_next) * ctx["s_noise"] * sigma_up
+
+
+def linear_multistep_coeff(order, t, i, j):
+    """gc_sampling.py:413-427: integral over [t_i, t_{i+1}] of the j-th Lagrange basis polynomial through the last `order` nodes"""
+    if order - 1 > i:
+        raise ValueError(f'Order {order} too high for step {i}')
+
+    def basis(tau):
+        prod = 1.
+        for k in range(order):
+            if k != j:
+                prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+    from scipy import integrate
+    return integrate.quad(basis, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+def _rule_lms(ctx, x, denoised, sigma, sigma_next):                        # :452-465: Adams-Bashforth in sigma over the derivative history
+    ds, i, order = ctx.setdefault("ds", []), ctx["i"], ctx["order"]
+    ds.append(to_d(x, sigma, denoised))
+    if len(ds) > order:
+        ds.pop(0)
+    cur = min(i + 1, order)
+    coeffs = [linear_multistep_coeff(cur, ctx["sigmas_np"], i, j) for j in range(cur)]
+    return x + sum(c * d for c, d in zip(coeffs, reversed(ds)))
+
+
+def _integrate(rule, model, state, x, goal, sigmas, scaler=None, extra_args=None, callback=None, cb_key="x", churn=None, eta=1., **more):
     extra_args = {} if extra_args is None else extra_args
     ones = x.new_ones([x.shape[0]])
     ctx = {"eta": eta, "eval": lambda xx, sig: model(state, xx, goal, sig * ones, **extra_args)}
+    ctx.update(more)
     n = len(sigmas) - 1
     for i in range(n):
+        ctx["i"] = i
         sigma_hat = sigmas[i]
         if churn is not None:               # Karras "churn": the reference draws eps every step, also when gamma == 0 (:195)
             s_churn, s_tmin, s_tmax, s_noise = churn
@@ -233,7 +303,57 @@ def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=
     return out if out is not None else _integrate(_rule_dpmpp_2m, model, state, action, goal, sigmas, None, extra_args, callback, "action")
 
 
+# ---- the remaining samplers of the reference module (two score evaluations per step or a derivative history): generic driver only ----
+
+def default_noise_sampler(x):
+    """gc_sampling.py:97-99"""
+    return lambda sigma, sigma_next: torch.randn_like(x)
+
+
+@torch.no_grad()
+def sample_dpm_2(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                 s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
+    """DPM-Solver-2 / Karras Algorithm 2 with the midpoint in log sigma (gc_sampling.py:315-372)."""
+    return _integrate(_rule_dpm_2, model, state, action, goal, sigmas, scaler, extra_args, callback, "action",
+                      churn=(s_churn, s_tmin, s_tmax, s_noise))
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.):
+    """Ancestral sampling with DPM-Solver-2 steps (gc_sampling.py:375-410)."""
+    return _integrate(_rule_dpm_2_ancestral, model, state, action, goal, sigmas, scaler, extra_args, callback, eta=eta)
+
+
+@torch.no_grad()
+def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, order=4):
+    """Linear multistep sampler (gc_sampling.py:430-466)."""
+    return _integrate(_rule_lms, model, state, action, goal, sigmas, scaler, extra_args, callback, order=order,
+                      sigmas_np=sigmas.detach().cpu().numpy())
+
+
+@torch.no_grad()
+def sample_dpmpp_2_with_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
+    """gc_sampling.py:797-831: the same update as sample_dpmpp_2m (the scaler is accepted and ignored there as well)."""
+    out = _fused(model, "dpmpp_2m", state, action, goal, sigmas, None, extra_args, callback)
+    return out if out is not None else _integrate(_rule_dpmpp_2m, model, state, action, goal, sigmas, None, extra_args, callback, "action")
+
+
+@torch.no_grad()
+def sample_dpmpp_2s(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.):
+    """DPM-Solver++(2S) (gc_sampling.py:956-994)."""
+    return _integrate(_rule_dpmpp_2s, model, state, action, goal, sigmas, scaler, extra_args, callback, "action")
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                              eta=1., s_noise=1., noise_sampler=None):
+    """Ancestral sampling with DPM-Solver++(2S) steps (gc_sampling.py:874-920)."""
+    return _integrate(_rule_dpmpp_2s_ancestral, model, state, action, goal, sigmas, scaler, extra_args, callback, "action", eta=eta,
+                      s_noise=s_noise, noise_sampler=default_noise_sampler(action) if noise_sampler is None else noise_sampler)
+
+
 SAMPLERS = {
     "ddim": sample_ddim, "euler": sample_euler, "heun": sample_heun, "dpmpp_2m": sample_dpmpp_2m,
-    "euler_ancestral": sample_euler_ancestral,
+    "euler_ancestral": sample_euler_ancestral, "dpm": sample_dpm_2, "ancestral": sample_dpm_2_ancestral, "lms": sample_lms,
+    "dpmpp_2s": sample_dpmpp_2s, "dpmpp_2s_ancestral": sample_dpmpp_2s_ancestral, "dpmpp_2_with_lms": sample_dpmpp_2_with_lms,
 }
