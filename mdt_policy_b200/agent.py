@@ -180,6 +180,10 @@ class DenoiseAgent:
             return partial(utils.rand_log_uniform, min_value=self.sigma_min, max_value=self.sigma_max)
         if kind == 'uniform':
             return partial(utils.rand_uniform, min_value=self.sigma_min, max_value=self.sigma_max)
+        if kind == 'v-diffusion':
+            return partial(utils.rand_v_diffusion, sigma_data=self.sigma_data, min_value=self.sigma_min, max_value=self.sigma_max)
+        # 'discrete' and 'split-lognormal' cannot be reached through the reference's make_sample_density either (float step count /
+        # list-indexed config, mdtv_agent.py:582-589); the underlying utils.rand_discrete / rand_split_log_normal are provided
         raise ValueError('Unknown sample density type')
 
     # mdtv_agent.py:508-521 (forward value; see GCDenoiser.loss about the backward pass)

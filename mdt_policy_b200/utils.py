@@ -39,3 +39,25 @@ def rand_log_uniform(shape, min_value, max_value, device="cpu", dtype=torch.floa
 def rand_uniform(shape, min_value, max_value, device="cpu", dtype=torch.float32):
     """utils.py:201-203"""
     return torch.rand(shape, device=device, dtype=dtype) * (max_value - min_value) + min_value
+
+
+def rand_v_diffusion(shape, sigma_data=1.0, min_value=0.0, max_value=float("inf"), device="cpu", dtype=torch.float32):
+    """utils.py:176-181 -- truncated v-diffusion density: uniform in the arctan CDF, mapped back with tan"""
+    cdf_lo = math.atan(min_value / sigma_data) * 2 / math.pi
+    cdf_hi = math.atan(max_value / sigma_data) * 2 / math.pi
+    u = torch.rand(shape, device=device, dtype=dtype) * (cdf_hi - cdf_lo) + cdf_lo
+    return torch.tan(u * math.pi / 2) * sigma_data
+
+
+def rand_split_log_normal(shape, loc, scale_1, scale_2, device="cpu", dtype=torch.float32):
+    """utils.py:184-191 -- half-normal magnitudes placed left (scale_1) or right (scale_2) of loc in log space"""
+    mag = torch.randn(shape, device=device, dtype=dtype).abs()
+    side = torch.rand(shape, device=device, dtype=dtype)
+    left = side < scale_1 / (scale_1 + scale_2)
+    return torch.where(left, loc - mag * scale_1, loc + mag * scale_2).exp()
+
+
+def rand_discrete(shape, values, device="cpu", dtype=torch.float32):
+    """utils.py:194-198 -- uniform draw from a 1-D tensor of candidate sigmas"""
+    idx = torch.randint(0, len(values), shape, device=device)
+    return values.index_select(0, idx).to(dtype)

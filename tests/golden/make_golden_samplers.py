@@ -36,6 +36,13 @@ def main():
         out[key] = fn(model, state, inp["x_T"], inp["goal"], sig, disable=True, **kw)
         out["rng_after_" + key] = torch.rand(2)
         assert torch.isfinite(out[key]).all(), key
+    # the three sigma densities of mdt/models/edm_diffusion/utils.py that r2_pins.npz does not cover
+    import importlib
+    rutils = importlib.import_module("mdt.models.edm_diffusion.utils")
+    torch.manual_seed(9)
+    out["density_v_diffusion"] = rutils.rand_v_diffusion((512,), sigma_data=0.5, min_value=0.001, max_value=80.0)
+    out["density_split_log_normal"] = rutils.rand_split_log_normal((512,), loc=-1.2, scale_1=0.8, scale_2=1.6)
+    out["density_discrete"] = rutils.rand_discrete((512,), gcs.get_sigmas_exponential(50, 0.001, 80.0))
     save("samplers", meta=dict(case="samplers", smp_seed=33, smp_input_seed=43), **out)
 
 

@@ -38,6 +38,21 @@ def test_restated_sampler_matches_reference_output_and_rng_stream(key, fn, kw):
     assert torch.equal(torch.rand(2), gold["rng_after_" + key])          # consumed exactly the reference's draws
 
 
+def test_remaining_sigma_densities_match_reference_streams():
+    """rand_v_diffusion / rand_split_log_normal / rand_discrete (utils.py:176-198) under the reference's seed; 'v-diffusion' through
+    DenoiseAgent.make_sample_density as mdtv_agent.py:577-580 builds it"""
+    import math
+    from mdt_policy_b200 import utils as U, DenoiseAgent
+    _, gold = H.load_golden("samplers")
+    torch.manual_seed(9)
+    assert torch.equal(U.rand_v_diffusion((512,), sigma_data=0.5, min_value=0.001, max_value=80.0), gold["density_v_diffusion"])
+    assert torch.equal(U.rand_split_log_normal((512,), loc=-1.2, scale_1=0.8, scale_2=1.6), gold["density_split_log_normal"])
+    assert torch.equal(U.rand_discrete((512,), gcs.get_sigmas_exponential(50, 0.001, 80.0)), gold["density_discrete"])
+    agent = DenoiseAgent(model=None, device="cpu", sigma_sample_density_type="v-diffusion")
+    torch.manual_seed(9)
+    assert torch.equal(agent.make_sample_density()(shape=(512,), device="cpu"), gold["density_v_diffusion"])
+
+
 def test_agent_dispatch_covers_the_reference_sampler_names():
     """mdtv_agent.py:619-656: every sampler_type the reference dispatches that works there is accepted (three are not: dpm_adaptive /
     dpm_fast raise NameError in the reference itself, dpmpp_2m_sde needs torchsde)"""
