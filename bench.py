@@ -155,6 +155,65 @@ def cpu_reference_run(enc, dec, B, steps, warmup, budget_s=150.0):
     return value, desc, total / steps * 1e3
 
 
+def small_batch_measure(agent, enc, dec, dev):
+    """the small-batch regime (B <= 32), where the path is bound by streaming the decoder-side weights once per step
+    (and by latency), not by the tensor cores.  10-step DDIM call latency at B = 1 and 32 on the GPU (device-resident inputs, median
+    over 50 calls), the oracle port's B = 1 latency on the host, and the roofline against the measured HBM copy bandwidth with
+    algorithmic bytes = decoder-side weights (13,597,831 fp32 at 4+4) + x in/out + context per step."""
+    from mdt_policy_b200.synthetic import synthetic_inputs
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm = float(json.load(f)["hbm_gbs"])
+        hbm_src = "measured copy bandwidth (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        hbm, hbm_src = 6500.0, "fallback (B200_PROFILING.md)"
+    out = {"what": "10-step DDIM sampling call, device-resident inputs, median of 50 calls", "hbm_peak_GBps": hbm, "peak_source": hbm_src}
+    dec_weight_bytes = 13_597_831 * 4 * dec / 4
+    for b in (1, 32):
+        inp = synthetic_inputs(b, seed=24)
+        state = {"state_images": inp["state_images"].to(dev), "modality": "lang"}
+        goal, xT = inp["goal"].to(dev), inp["x_T"].to(dev)
+        for _ in range(5):
+            agent.denoise_actions(None, state, goal, inference=True, x_T=xT)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(50):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            agent.denoise_actions(None, state, goal, inference=True, x_T=xT)
+            e.record(); e.synchronize()
+            ms.append(s.elapsed_time(e))
+        ms.sort()
+        med = ms[len(ms) // 2]
+        alg_bytes = N_STEPS * (dec_weight_bytes + 2 * b * 280 + b * 6144)
+        out[f"B{b}"] = {"ms_per_call": med, "p95_ms": ms[int(0.95 * (len(ms) - 1))], "denoise_steps_per_s": N_STEPS / (med / 1e3),
+                        "roofline": {"bound": "hbm", "achieved": alg_bytes / (med / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                     "frac": alg_bytes / (med / 1e3) / 1e9 / hbm, "alg_bytes_per_call": alg_bytes}}
+    try:      # host latency of the same B = 1 call (oracle port, thread count as calibrated by cpu_reference_run would pick: try 8 / all)
+        from oracle import mdt_oracle as orc
+        from mdt_policy_b200.synthetic import synthetic_state_dict
+        from mdt_policy_b200 import GCDenoiser
+        shapes = [(n, p.shape) for n, p in GCDenoiser(inner_cfg(enc, dec, "fp32", 1), sigma_data=0.5).named_parameters()]
+        P = synthetic_state_dict(shapes, 12, "trained")
+        cfg = orc.OracleCfg(n_enc_layers=enc, n_dec_layers=dec)
+        inp = synthetic_inputs(1, seed=24)
+        sig = orc.get_sigmas_exponential(N_STEPS, SIGMA_MIN, SIGMA_MAX)
+        best, best_c = None, None
+        for c in sorted({min(8, os.cpu_count() or 1), os.cpu_count() or 1}):
+            torch.set_num_threads(c)
+            ts = []
+            for _ in range(4):
+                t0 = time.perf_counter()
+                orc.sample(P, cfg, {"state_images": inp["state_images"], "modality": "lang"}, inp["x_T"], inp["goal"], sig, "ddim")
+                ts.append(time.perf_counter() - t0)
+            if best is None or min(ts[1:]) < best:
+                best, best_c = min(ts[1:]), c
+        out["cpu_B1"] = {"ms_per_call": best * 1e3, "cores": best_c, "kind": "port"}
+    except Exception as e:  # noqa: BLE001
+        out["cpu_B1"] = {"error": repr(e)}
+    return out
+
+
 def perceiver_measure(dev, B):
     """the PerceiverResampler that produces the denoiser's 3 state tokens from the (B, 1, 392, 384) Voltron token
     sequence (shipped config: depth 6, 8 heads x 64) -- per-chunk latency next to the sampling call it precedes."""
@@ -668,7 +727,8 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["dominant_kernel"] = {"error": repr(e)}
     if world == 1:
-        for name, fn in (("variant_6x6", lambda: variant_6x6(args, dev, B)), ("gpu_torch_baseline", lambda: gpu_torch_baseline(enc, dec, B, dev)),
+        for name, fn in (("small_batch", lambda: small_batch_measure(agent, enc, dec, dev)),
+                         ("variant_6x6", lambda: variant_6x6(args, dev, B)), ("gpu_torch_baseline", lambda: gpu_torch_baseline(enc, dec, B, dev)),
                          ("train", lambda: train_measure(args, dev, 512, 10, 3)), ("perceiver", lambda: perceiver_measure(dev, B))):
             if os.environ.get("MDTB200_BENCH_SKIP_EXTRAS"):
                 break

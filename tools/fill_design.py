@@ -17,6 +17,9 @@ rows = [
      f"{rf['achieved']:.1f} TFLOP/s, frac **{rf['frac']:.4f}**"),
     ("`dominant_kernel` = `tc::tc_gemm_kernel`, timed live at the per-chain M = 640 the graph runs, tile width as `launch_tc_gemm` picks it, non-zero operands, launch-weighted over the 4 GEMMs of a layer",
      f"{dk['achieved']:.1f} TFLOP/s algorithmic, frac {dk['frac']:.4f} (" + ", ".join(f"{k} {v:.1f} us" for k, v in sh.items()) + f"); `traffic` {rf['traffic'] / 1e6:.2f} MB DRAM per launch = the algorithmic operand bytes (profiles/r02_gemm_traffic.json)"),
+    ("`small_batch` (the weight-streaming / latency regime of SURVEY 8d; `hbm` roofline with algorithmic bytes = decoder weights + x + context per step)",
+     " ; ".join(f"B={b}: {d['small_batch'][f'B{b}']['ms_per_call']:.2f} ms per 10-step call, {d['small_batch'][f'B{b}']['roofline']['achieved']:.0f} GB/s = frac {d['small_batch'][f'B{b}']['roofline']['frac']:.3f}" for b in (1, 32))
+     + f" ; host (oracle port) B=1: {d['small_batch']['cpu_B1'].get('ms_per_call', float('nan')):.0f} ms") if "small_batch" in d and "B1" in d["small_batch"] else ("`small_batch`", "n/a"),
     ("`variant_6x6` (BASELINE-literal 6 enc + 6 dec)", f"{d['variant_6x6']['value']:.0f} steps/s ({d['variant_6x6']['ms_per_step']:.2f} ms)"),
     ("`gpu_torch_baseline`: the same algorithm as stock PyTorch on the same B200 (oracle port's ATen ops on cuda, encoder per evaluation like the reference)",
      f"eager fp32 {tb['eager_fp32']['value']:.0f} steps/s, CUDA-graphed fp32 {tb['graphed_fp32']['value']:.0f}, TF32 {tb['tf32']['value']:.0f} (action error {tb['tf32']['err']:.1e} vs the 1e-4 gate) -> this repo is {d['value'] / tb['graphed_fp32']['value']:.1f}x the graphed fp32 arm"),
