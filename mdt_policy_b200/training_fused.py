@@ -62,9 +62,33 @@ def _bank(net):
         add(f"dec{i}.fc", [b.mlp.c_fc]); add(f"dec{i}.proj", [b.mlp.c_proj])
     add("dec.xkv", [m for b in net.decoder.blocks for m in (b.cross_att.key, b.cross_att.value)])
     add("dec.mod", [b.adaLN_zero.modulation[1] for b in net.decoder.blocks])
+    # the embedding MLPs / token embeddings (goal, language goal, state tokens, sigma): one group per Linear whose dims allow the tensor cores
+    seen = set()
+    for name, mod in _embedding_linears(net):
+        w = mod.weight
+        if id(w) not in seen and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0:
+            seen.add(id(w))
+            add(name, [mod])
     bank = O.WeightBank(groups, dev)
     net.__dict__["_train_bank"] = bank
     return bank
+
+
+def _embedding_linears(net):
+    out = [("emb.goal0", net.goal_emb[0]), ("emb.goal2", net.goal_emb[2]), ("emb.lang0", net.lang_emb[0]), ("emb.lang2", net.lang_emb[2]),
+           ("emb.tok", net.tok_emb), ("emb.sig1", net.sigma_emb[1]), ("emb.sig3", net.sigma_emb[3])]
+    if getattr(net, "incam_embed", None) is not None:
+        out.append(("emb.incam", net.incam_embed))
+    return out
+
+
+def _emb_lin(net, bank, mod, x):
+    """Linear of an embedding path: through the weight bank (one split of x, pre-split weight) when the module is in it"""
+    name = net.__dict__.setdefault("_emb_names", {}).get(id(mod.weight))
+    if name is None:
+        name = next((n for n, m in _embedding_linears(net) if m.weight is mod.weight and n in bank.w16), "")
+        net.__dict__["_emb_names"][id(mod.weight)] = name
+    return linear_group(x, bank, name, [mod]) if name else T._lin(mod, x)
 
 
 def _rows(ws):
@@ -331,12 +355,12 @@ def encode_train(net, states, goals):
     train = net.training
     lang = net.use_modality_encoder and states.get("modality") == "lang" and net._variant == "mdtv"
     gm = net.lang_emb if lang else net.goal_emb
-    g = T._lin(gm[2], T.Act.apply(T._lin(gm[0], goals[:, :1, :].float()), T.ACT_GELU))
+    g = _emb_lin(net, bank, gm[2], T.Act.apply(_emb_lin(net, bank, gm[0], goals[:, :1, :].float()), T.ACT_GELU))
     if net._variant == "mdtv":
-        s = T._lin(net.tok_emb, states["state_images"].float())
+        s = _emb_lin(net, bank, net.tok_emb, states["state_images"].float())
     else:
-        st = T._lin(net.tok_emb, states["static"].float())
-        gr = T._lin(net.incam_embed, states["gripper"].float())
+        st = _emb_lin(net, bank, net.tok_emb, states["static"].float())
+        gr = _emb_lin(net, bank, net.incam_embed, states["gripper"].float())
         s = torch.cat((st, gr), dim=1)
         g = T._drop(g + net.pos_emb[:, : net.goal_seq_len, :], net.drop.p if train else 0.0)
         s = T._drop(s + net.pos_emb[:, net.goal_seq_len: net.goal_seq_len + 1, :], net.drop.p if train else 0.0)
@@ -362,7 +386,7 @@ def decode_train(net, ctx, actions, sigma):
     f = torch.exp(torch.arange(half, device=sigma.device, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
     ang = e[:, None] * f[None, :]
     pe = torch.cat((ang.sin(), ang.cos()), dim=-1)                       # no parameters, no gradient: input preparation
-    c = T._lin(net.sigma_emb[3], T.Act.apply(T._lin(net.sigma_emb[1], pe), T.ACT_MISH))            # (B, d)
+    c = _emb_lin(net, bank, net.sigma_emb[3], T.Act.apply(_emb_lin(net, bank, net.sigma_emb[1], pe), T.ACT_MISH))            # (B, d)
     sc_c = T.Act.apply(c, T.ACT_SILU)
     train = net.training
     blocks = list(net.decoder.blocks)

@@ -20,7 +20,7 @@ open(root + "profiles/r02_train_summary.md", "w").write(f"""# Round 2: training 
 
 Bench sub-record (`profiles/r02_final_bench.json` -> `train`): **{b['graphed']['ms_per_step']:.2f} ms per step replayed as one CUDA graph**
 (`GraphedTrainStep`: loss + backward + optimizer; {b['graphed']['value'] / 1e3:.0f} k action-tokens/s), {b['eager']['ms_per_step']:.2f} ms eager (host-bound: ~390 launches + autograd from
-Python). Loss {b['eager']['loss_first']:.3f} -> {b['eager']['loss_last']:.3f} over the timed eager steps.  2 GPUs, data-parallel replay: 4.74 ms (profiles/r02_2gpu_train.json).
+Python). Loss {b['eager']['loss_first']:.3f} -> {b['eager']['loss_last']:.3f} over the timed eager steps.  2 GPUs, data-parallel replay: 4.26 ms (profiles/r02_2gpu_train.json).
 
 History (graph replay unless noted; details in profiles/r02_experiments.md): round 1 13.9 ms eager (and invalid beyond a few steps: W-prefetch
 race, fixed) -> 11.7 ms captured (760 kernels: the step was GPU-bound, not host-bound) -> 5.83 (one autograd node per residual branch,
