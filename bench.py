@@ -234,9 +234,30 @@ def perceiver_measure(dev, B):
     # algorithmic FLOPs of the REFERENCE formulation per sample and layer: K/V projections of 395 tokens, q, scores, PV, to_out, FF
     d, I, F, Q = 384, 512, 392, 3
     per_layer = 2 * (2 * (F + Q) * d * I + Q * d * I + 2 * Q * (F + Q) * I + Q * I * d + 2 * Q * d * 4 * d)
-    return {"workload": f"PerceiverResampler depth 6, B={B}, 392 feature tokens -> 3 latents (random weights / inputs)", "ms_per_call": ms,
-            "launches_per_call": (m.launch_count() - l0) // k, "reference_formulation_gflop": 6 * per_layer * B / 1e9,
-            "note": "queries are projected into feature space, so ~21x fewer FLOPs are executed than the reference formulation counts"}
+    rec = {"workload": f"PerceiverResampler depth 6, B={B}, 392 feature tokens -> 3 latents (random weights / inputs)", "ms_per_call": ms,
+           "launches_per_call": (m.launch_count() - l0) // k, "reference_formulation_gflop": 6 * per_layer * B / 1e9,
+           "note": "queries are projected into feature space, so ~21x fewer FLOPs are executed than the reference formulation counts"}
+    try:        # the honest GPU competitor: the reference formulation (oracle port = the reference's ATen ops) as stock PyTorch on this GPU
+        from oracle import perceiver_oracle as po
+        P = {n: p.detach() for n, p in m.named_parameters()}
+        prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            ref = po.perceiver_forward(P, x, 6)
+            got = m(x)
+            for _ in range(2):
+                po.perceiver_forward(P, x, 6)
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(5):
+                po.perceiver_forward(P, x, 6)
+            e.record(); torch.cuda.synchronize()
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        rec["gpu_torch_eager_fp32"] = {"ms_per_call": s.elapsed_time(e) / 5, "max_abs_diff_vs_this_repo": float((got - ref).abs().max())}
+    except Exception as ex:  # noqa: BLE001
+        rec["gpu_torch_eager_fp32"] = {"error": repr(ex)[:200]}
+    return rec
 
 
 def train_measure(args, dev, B=512, steps=10, warmup=3):
