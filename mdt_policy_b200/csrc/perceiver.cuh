@@ -185,6 +185,109 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
   mma_tf32(d, ah, bh0, bh1);
 }
 
+// ---- q-path on the warp-level tensor cores (3xTF32, fp32-grade like the SIMT kernel above, which stays as MDTB200_PERC_QPATH=simt) ----
+// (1) [q | k] = lhat . [Wq ; Wk]^T : CTA = 64 latent rows x one 64-column block (columns of q for blockIdx.y < H, of k otherwise),
+//     warp = 16 rows x 64 columns (8 n-tiles); A and B fragments are streamed from global memory as 16-byte loads with the k-permutation
+//     of the scores kernel (lane t owns reduction indices 4t..4t+3 of a 16-wide chunk = k (t, t+4) of two consecutive k-steps).
+//     q is scaled and its score constant cq[row, h] = q_h . (Wk_h b) is reduced from the accumulators.
+__global__ void __launch_bounds__(128) perceiver_qk_mma_kernel(QPathArgs a) {
+  pdl_enter();
+  const int d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int cb = blockIdx.y, is_k = cb >= a.H, h = is_k ? cb - a.H : cb;
+  const int r_a = blockIdx.x * 64 + warp * 16 + g, r_b = r_a + 8;
+  const float* W = (is_k ? a.Wk : a.Wq) + (size_t)h * 64 * d;
+  const float* xa = a.lhat + (size_t)(r_a < a.Mq ? r_a : a.Mq - 1) * d + 4 * t;
+  const float* xb = a.lhat + (size_t)(r_b < a.Mq ? r_b : a.Mq - 1) * d + 4 * t;
+  const float* wp = W + (size_t)g * d + 4 * t;
+  float acc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll 2
+  for (int j = 0; j < d / 16; ++j) {
+    const float4 va = __ldg(reinterpret_cast<const float4*>(xa + 16 * j)), vb = __ldg(reinterpret_cast<const float4*>(xb + 16 * j));
+    float4 wv[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) wv[n] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)n * 8 * d + 16 * j));
+    uint32_t ah0[4], al0[4], ah1[4], al1[4];
+    tf32_split(va.x, ah0[0], al0[0]); tf32_split(vb.x, ah0[1], al0[1]); tf32_split(va.y, ah0[2], al0[2]); tf32_split(vb.y, ah0[3], al0[3]);
+    tf32_split(va.z, ah1[0], al1[0]); tf32_split(vb.z, ah1[1], al1[1]); tf32_split(va.w, ah1[2], al1[2]); tf32_split(vb.w, ah1[3], al1[3]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      uint32_t bh[4], bl[4];
+      tf32_split(wv[n].x, bh[0], bl[0]); tf32_split(wv[n].y, bh[1], bl[1]); tf32_split(wv[n].z, bh[2], bl[2]); tf32_split(wv[n].w, bh[3], bl[3]);
+      mma_3x(acc[n], ah0, al0, bh[0], bh[1], bl[0], bl[1]);
+      mma_3x(acc[n], ah1, al1, bh[2], bh[3], bl[2], bl[3]);
+    }
+  }
+  float cqa = 0.f, cqb = 0.f;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = n * 8 + 2 * t + (i & 1), row = (i & 2) ? r_b : r_a;
+      const float v = is_k ? acc[n][i] : acc[n][i] * a.scale;
+      if (!is_k) { const float kbv = a.kb[h * 64 + c]; if (i & 2) cqb = fmaf(v, kbv, cqb); else cqa = fmaf(v, kbv, cqa); }
+      if (row < a.Mq) a.qkv[(size_t)row * a.ldq + (is_k ? a.inner : 0) + h * 64 + c] = v;
+    }
+  }
+  if (!is_k) {
+    cqa += __shfl_xor_sync(0xffffffffu, cqa, 1); cqa += __shfl_xor_sync(0xffffffffu, cqa, 2);
+    cqb += __shfl_xor_sync(0xffffffffu, cqb, 1); cqb += __shfl_xor_sync(0xffffffffu, cqb, 2);
+    if (t == 0) {
+      if (r_a < a.Mq) a.cq[(size_t)r_a * a.H + h] = cqa;
+      if (r_b < a.Mq) a.cq[(size_t)r_b * a.H + h] = cqb;
+    }
+  }
+}
+// (2) qtilde_h = g (.) (q_h . Wk_h) : CTA = 64 rows x 128 feature-space columns of head h (grid (Mq/64, d/128, H)), warp = 16 rows x 128
+//     columns = 4 groups of four n-tiles whose B fragments come from one 16-byte load per k row (lane g owns columns 4g..4g+3 of a
+//     32-column group: column 4g + u is index g of n-tile u).  K = 64 (the head dimension).
+__global__ void __launch_bounds__(128) perceiver_qt_mma_kernel(QPathArgs a) {
+  pdl_enter();
+  const int d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.z, c0 = blockIdx.y * 128;
+  const int r_a = blockIdx.x * 64 + warp * 16 + g, r_b = r_a + 8;
+  const float* qa = a.qkv + (size_t)(r_a < a.Mq ? r_a : a.Mq - 1) * a.ldq + h * 64 + 4 * t;
+  const float* qb = a.qkv + (size_t)(r_b < a.Mq ? r_b : a.Mq - 1) * a.ldq + h * 64 + 4 * t;
+  const float* wk = a.Wk + (size_t)(h * 64 + 4 * t) * d + c0 + 4 * g;          // k row 4t (+0..3) of the chunk, columns 4g..4g+3 of group 0
+  float acc[16][4];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {                 // 16 reduction indices per chunk
+    const float4 va = *reinterpret_cast<const float4*>(qa + 16 * j), vb = *reinterpret_cast<const float4*>(qb + 16 * j);
+    uint32_t ah0[4], al0[4], ah1[4], al1[4];
+    tf32_split(va.x, ah0[0], al0[0]); tf32_split(vb.x, ah0[1], al0[1]); tf32_split(va.y, ah0[2], al0[2]); tf32_split(vb.y, ah0[3], al0[3]);
+    tf32_split(va.z, ah1[0], al1[0]); tf32_split(vb.z, ah1[1], al1[1]); tf32_split(va.w, ah1[2], al1[2]); tf32_split(vb.w, ah1[3], al1[3]);
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+      float4 w[4];                               // k rows 4t + 0..3 of this chunk
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(reinterpret_cast<const float4*>(wk + (size_t)(16 * j + kk) * d + grp * 32));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float b00 = u == 0 ? w[0].x : u == 1 ? w[0].y : u == 2 ? w[0].z : w[0].w;      // k = t   (row 4t)     step 0
+        const float b01 = u == 0 ? w[1].x : u == 1 ? w[1].y : u == 2 ? w[1].z : w[1].w;      // k = t+4 (row 4t + 1) step 0
+        const float b10 = u == 0 ? w[2].x : u == 1 ? w[2].y : u == 2 ? w[2].z : w[2].w;      // step 1
+        const float b11 = u == 0 ? w[3].x : u == 1 ? w[3].y : u == 2 ? w[3].z : w[3].w;
+        uint32_t h0, l0, h1, l1;
+        tf32_split(b00, h0, l0); tf32_split(b01, h1, l1);
+        mma_3x(acc[grp * 4 + u], ah0, al0, h0, h1, l0, l1);
+        tf32_split(b10, h0, l0); tf32_split(b11, h1, l1);
+        mma_3x(acc[grp * 4 + u], ah1, al1, h0, h1, l0, l1);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = c0 + (n >> 2) * 32 + 4 * (2 * t + (i & 1)) + (n & 3), row = (i & 2) ? r_b : r_a;
+      if (row < a.Mq) a.qt[((size_t)h * a.Mp + row) * d + col] = acc[n][i] * a.g[col];
+    }
+  }
+}
+
 // scores[b, r, f] = qtilde[r] . xhat[b, f] + cq[r]      r = h*Q + q < HQ <= 8 NT.   CTA = 64 features of one sample, warp = 16 of
 // them (one m-tile); the feature-space queries sit in shared memory as tf32 hi / lo planes, the features stream from global memory
 // straight into the A fragments (each xhat element is used by exactly one warp) as 16-byte loads: within a 16-column chunk lane t

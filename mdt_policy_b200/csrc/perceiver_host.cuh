@@ -248,8 +248,15 @@ MDTB200_API int mdtb200_perceiver_forward(MdtPerceiver* h, const float* x_f, con
     TRY(pln(h, h->L, h->lnf, h->a16, L.nl_w, L.nl_b, Mq, st));
     {   // exact-fp32 score path: q (scaled), latent keys, feature-space queries, score constants
       pr::QPathArgs a{h->lnf, L.wq, L.wk, L.gm, L.kb, h->qkv, 3 * I, I, h->qt, h->cq, Mq, Mp, H, d, 1.0f / sqrtf(64.0f)};
-      launch_pdl(pr::perceiver_qpath_kernel<384>, dim3((Mq + pr::QP_ROWS - 1) / pr::QP_ROWS, H), dim3(256), 0, st, a);
-      TRY(pcheck(h, "perceiver_qpath_kernel"));
+      static const bool simt = getenv("MDTB200_PERC_QPATH") && !strcmp(getenv("MDTB200_PERC_QPATH"), "simt");
+      if (simt) {
+        launch_pdl(pr::perceiver_qpath_kernel<384>, dim3((Mq + pr::QP_ROWS - 1) / pr::QP_ROWS, H), dim3(256), 0, st, a);
+      } else {      // 3xTF32 tensor-core kernels: [q | k] projection (+ cq), then the feature-space queries
+        launch_pdl(pr::perceiver_qk_mma_kernel, dim3((Mq + 63) / 64, 2 * H), dim3(128), 0, st, a);
+        launch_pdl(pr::perceiver_qt_mma_kernel, dim3((Mq + 63) / 64, d / 128, H), dim3(128), 0, st, a);
+        h->launches += 1;
+      }
+      TRY(pcheck(h, "perceiver q-path kernels"));
     }
     {   // v_lat = LN(latents) . Wv^T  (value path: tensor cores)
       tc::TcGemm t{};

@@ -25,7 +25,8 @@ rows = [
      f"eager fp32 {tb['eager_fp32']['value']:.0f} steps/s, CUDA-graphed fp32 {tb['graphed_fp32']['value']:.0f}, TF32 {tb['tf32']['value']:.0f} (action error {tb['tf32']['err']:.1e} vs the 1e-4 gate) -> this repo is {d['value'] / tb['graphed_fp32']['value']:.1f}x the graphed fp32 arm"),
     ("`train` (config 3: batch 512, loss fwd + bwd + fused AdamW/EMA, shipped dropout)",
      f"**{tr['graphed']['ms_per_step']:.2f} ms per step** as a replayed CUDA graph (`GraphedTrainStep`) = {tr['graphed']['value'] / 1e3:.0f} k action-tokens/s; {tr['eager']['ms_per_step']:.2f} ms eager (host-bound) (round 1: 13.9-15.7 ms)"),
-    ("`perceiver` (8f-1: depth 6, 392 tokens -> 3 latents, B=256)", f"{d['perceiver']['ms_per_call']:.2f} ms per call, {d['perceiver']['launches_per_call']} launches"),
+    ("`perceiver` (8f-1: depth 6, 392 tokens -> 3 latents, B=256)", f"{d['perceiver']['ms_per_call']:.2f} ms per call, {d['perceiver']['launches_per_call']} launches"
+     + (f"; the reference formulation as stock PyTorch fp32 on the same GPU: {d['perceiver']['gpu_torch_eager_fp32']['ms_per_call']:.1f} ms" if 'ms_per_call' in d['perceiver'].get('gpu_torch_eager_fp32', {}) else "")),
     ("CPU arm (`cpu_baseline`, oracle port, thread count calibrated)", f"{cpu.get('value', float('nan')):.1f} steps/s on {cpu.get('cores', '?')} threads -> e2e is {d['e2e']['value'] / cpu.get('value', float('nan')):.0f}x"),
     ("clocks during the timed region", f"{d['clocks']['sm_mhz']:.0f} MHz of {d['clocks']['sm_max_mhz']:.0f}, throttle reasons {d['clocks']['reasons']}"),
 ]
