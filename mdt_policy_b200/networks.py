@@ -361,6 +361,8 @@ class _ScoreNetBase(nn.Module):
             if uncond:
                 goals = torch.zeros_like(goals)
             return training.forward_train(self, states, actions, goals, sigma)
+        if actions.shape[0] == 0:       # empty batch: nothing to launch (the reference's tensor ops return an empty result as well)
+            return actions.new_zeros(actions.shape, dtype=torch.float32)
         eng, _ = self._encode(states, goals, uncond, context_only=False)
         return self._decode(eng, actions, sigma, _precondition)
 
@@ -385,6 +387,8 @@ class _ScoreNetBase(nn.Module):
         """noise / eta: euler_ancestral only -- noise (n_steps, B, T, A) holds the standard-normal draw of every step (zeros where the
         reference draws nothing), produced by the caller so that the RNG stream is the reference's (gc_sampling.sample_euler_ancestral)."""
         self._check_mode()
+        if x_t.shape[0] == 0:
+            return x_t.new_zeros(x_t.shape, dtype=torch.float32)
         state = self._prep_state(states)
         goal = self._prep_goal(goals, self._states_length(states), bool(uncond))
         B = state.shape[0]

@@ -251,3 +251,15 @@ def test_multi_branch_ragged_fused_vs_generic(variant, B):
         loop = fn(model, state, inp["x_T"], inp["goal"], sig, disable=True, callback=lambda d: None)
         assert torch.isfinite(fused).all()
         assert (fused - loop).abs().max() < 3e-5, (fn.__name__, float((fused - loop).abs().max()))
+
+
+def test_empty_batch_returns_empty_actions():
+    """B = 0 (e.g. a rollout step in which no environment is due): no launch, an empty (0, T, A) result like the reference's tensor ops"""
+    from mdt_policy_b200 import gc_sampling as gcs
+    model = H.build_product(H.mdtv_inner_cfg(1, 1), 5, "trained")
+    state = {"state_images": torch.zeros(0, 3, 384, device="cuda"), "modality": "lang"}
+    x, g = torch.zeros(0, 10, 7, device="cuda"), torch.zeros(0, 1, 512, device="cuda")
+    sig = gcs.get_sigmas_exponential(4, 0.01, 80.0).cuda()
+    assert gcs.sample_ddim(model, state, x, g, sig).shape == (0, 10, 7)
+    with torch.no_grad():
+        assert model(state, x, g, torch.zeros(0, device="cuda")).shape == (0, 10, 7)

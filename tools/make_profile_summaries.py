@@ -55,7 +55,8 @@ feature-space formulation executes ~21x fewer).  History: 3.75 ms (SIMT score / 
 inner loops, one shared-memory round trip per 12 FMAs) -> cp.async staging made it WORSE (740 us: the loop, not the loads, was the
 problem) -> warp-level tensor cores, `mma.sync.m16n8k8` 3xTF32 with the features streamed from global memory into the A fragments
 (105 + 138 us) -> register prefetch ring (117 + 99 us, 2.13 ms) -> q-path weight chunks double-buffered (2.07 ms) -> 8-warp CTAs sharing
-one copy of the query planes in the scores kernel (95 + 98 us) = 1.94 ms per call.
+one copy of the query planes in the scores kernel, then in the weighted-sum kernel (95 + 92 us, 1.88 ms) -> q-path on 3xTF32 MMAs =
+{pb['ms_per_call']:.2f} ms per call.  The reference formulation as stock PyTorch (fp32, eager) on the same GPU: {pb.get('gpu_torch_eager_fp32', {}).get('ms_per_call', float('nan')):.1f} ms.
 
 ## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python tools/perceiver_once.py`; three forward calls)
 
@@ -71,6 +72,6 @@ one copy of the query planes in the scores kernel (95 + 98 us) = 1.94 ms per cal
 Both read xhat exactly once (traffic = algorithmic) and sit at ~4x the 24 us HBM time of that read: latency-bound at 12-16 warps per SM.
 Next: bf16 m16n8k16 hi/lo planes (half the shared-memory footprint -> twice the occupancy) or a tcgen05 formulation with the 24 query
 rows of two samples stacked into one N = 64 tile; `perceiver_qpath_kernel` (54 us per layer: exact-fp32 q, latent keys, feature-space
-queries for B x 3 rows) is the next largest item.
+queries for B x 3 rows; now two 3xTF32 MMA kernels) is the next largest item.
 """)
 print("ok")
