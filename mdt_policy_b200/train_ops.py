@@ -53,7 +53,9 @@ def split(x2d, h=None, act=0, want_colsum=False):
 
 
 class SplitKWorkspace:
-    """fp32 partial-tile workspace + per-tile arrival counters for the deterministic split-K weight-gradient GEMM (per device)."""
+    """fp32 partial-tile workspace + per-tile arrival counters for the deterministic split-K GEMMs, one per device and stream role.
+    Split-K launches that share a workspace must be ordered on ONE stream (they are: slot 0 = the caller's stream, slot 1 = the
+    weight-gradient side stream); training two models concurrently from two host threads on the same device is not supported."""
     _inst = {}
 
     def __init__(self, device):
@@ -299,7 +301,8 @@ class WeightBank:
             self.w16[name] = self.arena16[o16:o16 + rows * 2 * K].view(rows, 2 * K)
             r = 0
             for w in ws:
-                assert w.shape[1] == K and w.is_contiguous() and w.dtype == torch.float32 and K % 4 == 0
+                if w.shape[1] != K or not w.is_contiguous() or w.dtype != torch.float32 or K % 4:
+                    raise RuntimeError(f"weight group '{name}': members must be contiguous fp32 (N_i, {K}) matrices")
                 dst = self.arena16.data_ptr() + (o16 + r * 2 * K) * 2
                 blocks += [(len(recs), c) for c in range((w.numel() + 4095) // 4096)]
                 recs.append(struct.pack("<QQqii", w.data_ptr(), dst, w.numel(), K, 0))
@@ -312,7 +315,8 @@ class WeightBank:
                 self.bias[name] = self.arena32[o32:o32 + n]
                 r = 0
                 for b in bs:
-                    assert b.numel() % 4 == 0 and b.is_contiguous()
+                    if b.numel() % 4 or not b.is_contiguous():
+                        raise RuntimeError(f"weight group '{name}': biases must be contiguous with a multiple of 4 elements")
                     blocks += [(len(recs), c) for c in range((b.numel() + 4095) // 4096)]
                     recs.append(struct.pack("<QQqii", b.data_ptr(), self.arena32.data_ptr() + (o32 + r) * 4, b.numel(), 0, 0))
                     self.params.append(b)

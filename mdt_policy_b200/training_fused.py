@@ -157,7 +157,8 @@ class AttnBranch(Function):
             q, k, v, ldq, ldkv, Tk = qkv, qkv[:, d:], qkv[:, 2 * d:], 3 * d, 3 * d, Tq
         else:
             qkv = O.gemm16(0, a16, bank.w16[n_in], M, d, d, bias=bank.bias[n_in])
-            assert kv.stride(-1) == 1 and kv.stride(0) == kv.shape[1] * kv.stride(1)
+            if kv.stride(-1) != 1 or kv.stride(0) != kv.shape[1] * kv.stride(1):
+                raise RuntimeError("cross-attention K|V must be a last-dim slice of a contiguous (B, Tk, *) tensor")
             q, k, v, ldq, ldkv, Tk = qkv, kv, kv[..., d:], d, kv.stride(1), kv.shape[1]
         y16 = O.attn_fwd16(q, ldq, k, v, ldkv, B, H, hd, Tq, Tk, causal, p_attn, seed_a)
         f = O.gemm16(0, y16, bank.w16[n_o], M, d, d, bias=bank.bias[n_o])
@@ -210,7 +211,8 @@ class AttnBranch(Function):
         gw = [dwi[i * d:(i + 1) * d] for i in range(n_w)] + [dwo]
         gb = ([dbi[i * d:(i + 1) * d] for i in range(n_w)] if has_bi else []) + ([dbo] if has_bo else [])
         grads = gw + gb
-        assert len(grads) == n_params
+        if len(grads) != n_params:
+            raise RuntimeError("internal: gradient list does not match the parameters passed to AttnBranch")
         return (dx.view(B, Tq, d), dkv, dshift, dscale, dgate, None, dlw, dlb, *grads)
 
 
@@ -256,7 +258,8 @@ class MLPBranch(Function):
         dx, dlw, dlb = O.ln_bwd2(x2, da, ln_w, ln_b, scale, scale.stride(0) if scale is not None else 0, dout2, dshift, dscale, 3 * d, Tq)
         O.wgrad_join(x2.device)
         grads = [dwf, dwp] + ([dbf] if has_bf else []) + ([dbp] if has_bp else [])
-        assert len(grads) == n_params
+        if len(grads) != n_params:
+            raise RuntimeError("internal: gradient list does not match the parameters passed to MLPBranch")
         return (dx.view(B, Tq, d), dshift, dscale, dgate, None, dlw, dlb, *grads)
 
 
