@@ -6,8 +6,8 @@ shared sigma embedding), but every node is one of the autograd Functions below w
 exact-fp32 CUDA kernels of libmdtb200.so (C ABI "training primitives": mdtb200_op_*).  Semantics are the reference's
 train-mode forward: dropout on the attention probabilities (attn_pdrop), after both c_proj projections (resid_pdrop,
 mlp_pdrop) and on the action embedding (embed_pdrob), goal masking (goal_drop).  Dropout masks come from a counter-based
-hash of (seed, element index) -- the seed of every site is drawn from torch's CPU generator, so torch.manual_seed makes a
-step reproducible -- and cannot equal the reference's Philox stream: with p = 0 gradients match the reference to fp32
+hash of (seed, element index) -- one base seed per forward pass is drawn from torch's CPU generator and every dropout site derives its
+own from it, so torch.manual_seed makes a step reproducible -- and cannot equal the reference's Philox stream: with p = 0 gradients match the reference to fp32
 rounding, with p > 0 the check is statistical (tests/test_gpu_training.py).
 """
 from __future__ import annotations
@@ -181,9 +181,27 @@ class LayerNormMod(Function):
         return dx, dw, db, dshift, dscale
 
 
+_seed_pool = [0, 0]       # [base seed of the current forward pass, sites served from it]
+
+
+def begin_forward_seeds():
+    """one draw from torch's CPU generator per forward pass (torch.manual_seed -> reproducible); the dropout sites of that pass take
+    base + k * golden-ratio increments (the mask hash mixes seed and element index, so consecutive seeds are independent streams)"""
+    _seed_pool[0] = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    _seed_pool[1] = 0
+
+
 def _new_seed() -> int:
-    """one 63-bit seed per dropout site and call, from torch's CPU generator (torch.manual_seed -> reproducible)"""
+    """63-bit seed of the next dropout site: derived from the forward pass' base seed when one is active (forward_train), else one
+    draw from torch's CPU generator per call"""
+    if _seed_pool[0]:
+        _seed_pool[1] += 1
+        return (_seed_pool[0] + _seed_pool[1] * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def end_forward_seeds():
+    _seed_pool[0] = 0
 
 
 class Dropout(Function):
@@ -370,6 +388,15 @@ def decode_train(net, ctx, actions, sigma):
 
 
 def forward_train(net, states, actions, goals, sigma):
+    if net.training:
+        begin_forward_seeds()
+    try:
+        return _forward_train(net, states, actions, goals, sigma)
+    finally:
+        end_forward_seeds()
+
+
+def _forward_train(net, states, actions, goals, sigma):
     fused = _fused(net)
     if fused is not None:
         return fused.forward_train(net, states, actions, goals, sigma)
