@@ -171,3 +171,14 @@ def load():
             raise RuntimeError(f"mdt_policy_b200: {path} has ABI {lib.mdtb200_abi_version()}, expected {ABI_VERSION}")
         _lib = lib
         return lib
+
+
+def current_stream_ptr(device_index) -> C.c_void_p:
+    """raw cudaStream_t of torch's current stream on `device_index` (None: the current device).  torch.cuda.current_stream() builds a
+    Stream object per call (~7 us; a training step makes 300+ such calls), torch._C._cuda_getCurrentRawStream returns the handle directly."""
+    import torch
+    idx = torch.cuda.current_device() if device_index is None else device_index
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(idx))
+    return C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)

@@ -151,7 +151,7 @@ class _Engine:
 
     @property
     def stream(self) -> C.c_void_p:
-        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index))      # raw handle: no Stream object per call
+        return _lib.current_stream_ptr(self.device.index)      # raw handle: no Stream object per call
 
     def sync_weights(self, owner: nn.Module, prefix: str = "inner_model."):
         # The module tree is static, so walk it once and keep (name, owning _parameters dict, leaf) triples; every call

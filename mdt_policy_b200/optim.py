@@ -141,7 +141,7 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                 rc = self._lib.mdtb200_op_adamw_ema(
                     C.c_void_p(table.data_ptr()), C.c_void_p(blocks.data_ptr()), blocks.shape[0], group["lr"], beta1, beta2, group["eps"],
                     group["weight_decay"], float(decay), int(use_ema), step_ptr,
-                    C.c_void_p(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device())))
+                    _lib.current_stream_ptr(dev.index))
             if rc != 0:
                 raise RuntimeError(f"mdtb200_op_adamw_ema failed ({rc}): {self._lib.mdtb200_last_error(None).decode()}")
             # the kernel writes the parameters through raw pointers: tell autograd / the inference engine's staleness check

@@ -24,7 +24,7 @@ def _p(t):
 def _stream(t):
     # raw handle of torch's current stream on the tensor's device (torch.cuda.current_stream() builds a Stream object: ~7 us per call,
     # 300+ calls per training step)
-    return C.c_void_p(torch._C._cuda_getCurrentRawStream(t.device.index if t.device.index is not None else torch.cuda.current_device()))
+    return _lib.current_stream_ptr(t.device.index)
 
 
 def _chk(rc, what):
