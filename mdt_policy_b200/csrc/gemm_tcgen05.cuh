@@ -605,7 +605,9 @@ inline const char* launch_tc_gemm(TmaEncoder& enc, const TcGemm& g, cudaStream_t
   // A "widest tile that still fills ~1 wave, else narrowest" policy was 11 % slower end to end and no better for training.
   const int mt = (g.M + BM - 1) / BM;
   const bool wide = mt >= 16 && g.N % 192 == 0 && (g.N / 192) * mt <= 148 && (g.N % 128 != 0 || (g.N / 128) * mt > 148);
-  int bn = wide ? 192 : (g.N % 128 == 0 && g.N >= 1024) ? 128 : 64;
+  // d-wide outputs (N < 1024): 128 columns once there are >= 4 row tiles (A/B at B = 256, three alternations on one box: 2448 vs 2408
+  // steps/s: fewer, fatter CTAs leave more SMs to the other chains), 64 columns for the few-row launches where the CTA count is the limit
+  int bn = wide ? 192 : (g.N % 128 == 0 && (g.N >= 1024 || mt >= 4)) ? 128 : 64;
   {   // experiment overrides: MDTB200_BN_D (GEMMs with N < 1024), MDTB200_BN_WIDE (N >= 1024)
     static const int ov_d = getenv("MDTB200_BN_D") ? atoi(getenv("MDTB200_BN_D")) : 0;
     static const int ov_w = getenv("MDTB200_BN_WIDE") ? atoi(getenv("MDTB200_BN_WIDE")) : 0;
