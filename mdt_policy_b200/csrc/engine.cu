@@ -504,6 +504,10 @@ int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mo
       ca.ln3_w = L.ln3_w; ca.ln3_b = L.ln3_b; ca.bco = L.bco; ca.ln2_w = L.ln2_w; ca.ln2_b = L.ln2_b;
       ca.shift = ml + 3 * d; ca.scale = ml + 4 * d; ca.mod_stride = mod_stride;
       ca.a16 = k.a16; ca.ld16 = 2 * d; ca.lo_off = d; ca.B = B; ca.T = T; ca.Tc = Tc; ca.H = h->H; ca.d = d;
+      {   // the predecessor is the tcgen05 O GEMM (cross_fused implies the tensor-core path): tables / parameters may be read early
+        static const int early = getenv("MDTB200_CROSS_EARLY") ? atoi(getenv("MDTB200_CROSS_EARLY")) : 1;
+        ca.early = tcp && early;
+      }
       const size_t smem = cross_row_smem_bytes(d, T, Tc, h->H);
       if (d == 384) launch_pdl(cross_row_kernel<3>, dim3(B), dim3(CR_THREADS), smem, st, ca);
       else launch_pdl(cross_row_kernel<4>, dim3(B), dim3(CR_THREADS), smem, st, ca);

@@ -591,27 +591,55 @@ struct CrossRowArgs {
   const float *ln3_w, *ln3_b, *bco, *ln2_w, *ln2_b, *shift, *scale; int mod_stride;
   __nv_bfloat16* a16; int ld16, lo_off;        // LN2 (+modulate) output: split-bf16 operand of c_fc
   int B, T, Tc, H, d;
+  int early;                                   // 1: tables / parameters are requested BEFORE the dependency wait (see the kernel)
 };
 constexpr int CR_THREADS = 384;
+constexpr int CR_TMAX = 12;                    // score accumulators per thread (T * 32 < CR_THREADS -> T <= 11)
+// work split of the two [T x H*Tc x d] products (template parameter VPL = d / 128)
+template <int VPL>
+struct CrossCfg {
+  static constexpr int d = VPL * 128, D4 = d / 4;
+  static constexpr int KSL = d / 32;                     // scores: 32-float slices of the feature axis (12 / 16), one per warp pass
+  static constexpr int NSPLIT = CR_THREADS / D4;         // output: threads per column quad (4 at d = 384, 3 at d = 512) ...
+  static constexpr int NSH = VPL == 3 ? 2 : 1;           // ... = halves of the (head, token) sum ...
+  static constexpr int NSR = NSPLIT / NSH;               // ... x row groups (2 / 3)
+  static constexpr int RGP = VPL == 3 ? 8 : 4;           // probability slots per row group (whole float4s)
+  static constexpr int RGMAX = VPL == 3 ? 6 : 4;         // rows per group the accumulators cover: NSR * RGMAX >= 11
+  static constexpr int PS = NSR * RGP;                   // floats per (head, token) row of the transposed probabilities
+};
 inline size_t cross_row_smem_bytes(int d, int T, int Tc, int H) {
-  return ((size_t)(2 * T + H * Tc) * (d + 4) + (size_t)T * H * Tc + 5 * (size_t)d) * sizeof(float);
+  const int HT = H * Tc;
+  return ((size_t)(2 * T + HT) * (d + 4) + (size_t)((T * HT + 3) & ~3) + (size_t)HT * 16 + (size_t)(d / 32) * T * HT + (size_t)((HT + 3) & ~3) + 5 * (size_t)d) * sizeof(float);
 }
 
-// One CTA per sample.  smem: z[T][d+4] (LN3 output), x[T][d+4] (residual rows), tab[H*Tc][d+4] (G, later U), p[T][H*Tc], prm[5][d]
+// One CTA per sample.  smem: z[T][d+4] (LN3 output, later the second half-sum of the output product), x[T][d+4] (residual rows),
+// tab[H*Tc][d+4] (G, later U), p[T][H*Tc] (scores), pt[H*Tc][PS] (probabilities, transposed), part[KSL][T][H*Tc] (score partials),
+// ct[H*Tc] (score constants), prm[5][d].
+// Both products are register-tiled so that the FMA pipe, not shared-memory bandwidth, bounds them: a scores thread owns one (head,
+// token) row of G over a 32-float slice and ALL T query rows (G float4 once per T x 4 FMAs, z as warp-wide broadcasts); an output
+// thread owns one column quad, 3..6 query rows and half (d = 384) or all of the (head, token) sum.
+// PDL: everything except the residual rows is written once per sampling call, long before this kernel's predecessor (a tcgen05 GEMM,
+// which releases its dependents only after its OWN dependency wait) could start; with a.early those operands are therefore requested
+// before griddepcontrol.wait and arrive while the predecessor drains its epilogue.
 template <int VPL>
 __global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
   extern __shared__ __align__(16) float cr_smem[];
-  constexpr int d = VPL * 128, DP = d + 4, D4 = d / 4;
+  using C = CrossCfg<VPL>;
+  constexpr int d = C::d, DP = d + 4, D4 = C::D4;
   const int T = a.T, Tc = a.Tc, H = a.H, HT = H * Tc;
   float* sz = cr_smem;
   float* sx = sz + T * DP;
   float* stab = sx + T * DP;
   float* sp = stab + HT * DP;
-  float* sprm = sp + T * HT;            // bco | ln2_w | ln2_b | shift | scale
+  float* spt = sp + ((T * HT + 3) & ~3);
+  float* spart = spt + HT * 16;
+  float* sct = spart + C::KSL * T * HT;
+  float* sprm = sct + ((HT + 3) & ~3);   // bco | ln2_w | ln2_b | shift | scale
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_enter(KT_CROSS);
-  // ---- 1. every global operand is requested up front: G and U rows (registers), the T residual rows + LN3 parameters (one warp
-  //         per row), the small parameter vectors (remaining warps -> shared memory)
+  pdl_trigger();
+  if (!a.early) pdl_wait(KT_CROSS);
+  // ---- 1. every global operand is requested up front: G and U rows (registers), LN3 parameters (one warp per row), the small
+  //         parameter vectors and score constants (remaining warps -> shared memory); then (after the wait) the T residual rows
   constexpr int TPT = 8;                // float4 of G (and of U) per thread: H*Tc*d/4 <= 8 * 384
   float4 g[TPT], u[TPT];
 #pragma unroll
@@ -626,11 +654,9 @@ __global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
   }
   float4 xr[VPL], w3[VPL], b3[VPL];
   if (warp < T) {
-    const float* xp = a.xh + ((size_t)b * T + warp) * d;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 4;
-      xr[i] = *reinterpret_cast<const float4*>(xp + c);
       w3[i] = *reinterpret_cast<const float4*>(a.ln3_w + c);
       b3[i] = a.ln3_b ? *reinterpret_cast<const float4*>(a.ln3_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -642,6 +668,14 @@ __global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
       float4 v = src ? *reinterpret_cast<const float4*>(src + c) : (which == 4 ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f));
       *reinterpret_cast<float4*>(sprm + e) = v;
     }
+    for (int e = tid - T * 32; e < HT; e += CR_THREADS - T * 32) sct[e] = a.ctab[(size_t)b * HT + e];
+  }
+  for (int e = tid; e < HT * 16; e += CR_THREADS) spt[e] = 0.f;      // unused probability slots stay zero
+  if (a.early) pdl_wait(KT_CROSS);
+  if (warp < T) {
+    const float* xp = a.xh + ((size_t)b * T + warp) * d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) xr[i] = *reinterpret_cast<const float4*>(xp + (i * 32 + lane) * 4);
   }
   // ---- 2. G -> shared memory; LN3 of the T rows -> z, raw rows -> x
 #pragma unroll
@@ -671,56 +705,116 @@ __global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
     }
   }
   __syncthreads();
-  // ---- 3. scores: one thread per (row i, head h, context token j); causal top-left mask j <= i
+  // ---- 3a. score partials: lane = (head, token) row of G, warp = 32-float feature slice, T accumulators per thread
+  for (int s = warp; s < C::KSL; s += CR_THREADS / 32) {
+    for (int hj = lane; hj < HT; hj += 32) {
+      float acc[CR_TMAX];
+#pragma unroll
+      for (int i = 0; i < CR_TMAX; ++i) acc[i] = 0.f;
+      const float* gp = stab + hj * DP + s * 32;
+      const float* zp = sz + s * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 gv = *reinterpret_cast<const float4*>(gp + c);
+#pragma unroll
+        for (int i = 0; i < CR_TMAX; ++i) {
+          if (i < T) {
+            const float4 zv = *reinterpret_cast<const float4*>(zp + i * DP + c);
+            acc[i] = fmaf(zv.x, gv.x, acc[i]); acc[i] = fmaf(zv.y, gv.y, acc[i]);
+            acc[i] = fmaf(zv.z, gv.z, acc[i]); acc[i] = fmaf(zv.w, gv.w, acc[i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CR_TMAX; ++i)
+        if (i < T) spart[(s * T + i) * HT + hj] = acc[i];
+    }
+  }
+  __syncthreads();
+  // ---- 3b. scores = sum of the slice partials (fixed order) + constant; causal top-left mask j <= i.  U -> shared memory (G is done)
   for (int e = tid; e < T * HT; e += CR_THREADS) {
     const int i = e / HT, hj = e % HT, j = hj % Tc;
     float sc = -INFINITY;
     if (j <= i) {
-      const float* zp = sz + i * DP;
-      const float* gp = stab + hj * DP;
       float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < d; c += 8) {
-        const float4 z0 = *reinterpret_cast<const float4*>(zp + c), g0 = *reinterpret_cast<const float4*>(gp + c);
-        const float4 z1 = *reinterpret_cast<const float4*>(zp + c + 4), g1 = *reinterpret_cast<const float4*>(gp + c + 4);
-        acc0 = fmaf(z0.x, g0.x, acc0); acc0 = fmaf(z0.y, g0.y, acc0); acc0 = fmaf(z0.z, g0.z, acc0); acc0 = fmaf(z0.w, g0.w, acc0);
-        acc1 = fmaf(z1.x, g1.x, acc1); acc1 = fmaf(z1.y, g1.y, acc1); acc1 = fmaf(z1.z, g1.z, acc1); acc1 = fmaf(z1.w, g1.w, acc1);
-      }
-      sc = (acc0 + acc1) + a.ctab[(size_t)b * HT + hj];
+#pragma unroll
+      for (int s = 0; s < C::KSL; s += 2) { acc0 += spart[s * T * HT + e]; acc1 += spart[(s + 1) * T * HT + e]; }
+      sc = (acc0 + acc1) + sct[hj];
     }
     sp[e] = sc;
   }
-  __syncthreads();
-  // ---- 4. U -> shared memory (G is no longer needed); softmax over j per (row, head)
 #pragma unroll
   for (int t = 0; t < TPT; ++t) {
     const int e = tid + t * CR_THREADS;
     if (e < HT * D4) *reinterpret_cast<float4*>(stab + (e / D4) * DP + (e % D4) * 4) = u[t];
   }
+  __syncthreads();
+  // ---- 4. softmax over j per (row, head) -> transposed probabilities pt[hj][row group][row in group]
+  const int RG = (T + C::NSR - 1) / C::NSR;       // rows per group of the output product
   if (tid < T * H) {
-    float* row = sp + (tid / H) * HT + (tid % H) * Tc;
+    const int i = tid / H, hh = tid % H;
+    const float* row = sp + i * HT + hh * Tc;
     float mx = -INFINITY;
     for (int j = 0; j < Tc; ++j) mx = fmaxf(mx, row[j]);
     float sum = 0.f;
-    for (int j = 0; j < Tc; ++j) { float ex = expf(row[j] - mx); row[j] = ex; sum += ex; }
+    for (int j = 0; j < Tc; ++j) sum += expf(row[j] - mx);
     const float inv = 1.0f / sum;
-    for (int j = 0; j < Tc; ++j) row[j] *= inv;
+    float* dst = spt + (size_t)(hh * Tc) * C::PS + (i / RG) * C::RGP + i % RG;
+    for (int j = 0; j < Tc; ++j) dst[j * C::PS] = expf(row[j] - mx) * inv;
   }
   __syncthreads();
   // ---- 5. x_i += sum_hj p_i,hj U_hj + b_co   (kept in shared memory for the LayerNorm below, written back to the residual stream)
-  for (int e = tid; e < T * D4; e += CR_THREADS) {
-    const int i = e / D4, c = (e % D4) * 4;
-    const float* pr = sp + i * HT;
-    float4 acc = *reinterpret_cast<const float4*>(sprm + c);
-    for (int hj = 0; hj < HT; ++hj) {
-      const float pj = pr[hj];
+  {
+    const int c = (tid % D4) * 4, grp = tid / D4;
+    const int rg = grp % C::NSR, hs = grp / C::NSR;
+    const int HH = (HT + C::NSH - 1) / C::NSH;
+    const int hj_end = (hs + 1) * HH < HT ? (hs + 1) * HH : HT;
+    float4 acc[C::RGMAX];
+#pragma unroll
+    for (int r = 0; r < C::RGMAX; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hj = hs * HH; hj < hj_end; ++hj) {
       const float4 uv = *reinterpret_cast<const float4*>(stab + hj * DP + c);
-      acc.x = fmaf(pj, uv.x, acc.x); acc.y = fmaf(pj, uv.y, acc.y); acc.z = fmaf(pj, uv.z, acc.z); acc.w = fmaf(pj, uv.w, acc.w);
+      const float* pp = spt + hj * C::PS + rg * C::RGP;
+      float pr[C::RGP];
+#pragma unroll
+      for (int r = 0; r < C::RGP; r += 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(pp + r);
+        pr[r] = pv.x; pr[r + 1] = pv.y; pr[r + 2] = pv.z; pr[r + 3] = pv.w;
+      }
+#pragma unroll
+      for (int r = 0; r < C::RGMAX; ++r) {
+        acc[r].x = fmaf(pr[r], uv.x, acc[r].x); acc[r].y = fmaf(pr[r], uv.y, acc[r].y);
+        acc[r].z = fmaf(pr[r], uv.z, acc[r].z); acc[r].w = fmaf(pr[r], uv.w, acc[r].w);
+      }
     }
-    const float4 x0 = *reinterpret_cast<const float4*>(sx + i * DP + c);
-    const float4 x1 = make_float4(x0.x + acc.x, x0.y + acc.y, x0.z + acc.z, x0.w + acc.w);
-    *reinterpret_cast<float4*>(sx + i * DP + c) = x1;
-    *reinterpret_cast<float4*>(a.xh + ((size_t)b * T + i) * d + c) = x1;
+    if (C::NSH == 2) {          // second half of the (head, token) sum -> z (free since the scores), added by the first half's thread
+      if (hs == 1) {
+#pragma unroll
+        for (int r = 0; r < C::RGMAX; ++r) {
+          const int i = rg * RG + r;
+          if (r < RG && i < T) *reinterpret_cast<float4*>(sz + i * DP + c) = acc[r];
+        }
+      }
+      __syncthreads();
+    }
+    if (hs == 0) {
+      const float4 bc = *reinterpret_cast<const float4*>(sprm + c);
+#pragma unroll
+      for (int r = 0; r < C::RGMAX; ++r) {
+        const int i = rg * RG + r;
+        if (r < RG && i < T) {
+          float4 o = acc[r];
+          if (C::NSH == 2) {
+            const float4 o2 = *reinterpret_cast<const float4*>(sz + i * DP + c);
+            o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w;
+          }
+          const float4 x0 = *reinterpret_cast<const float4*>(sx + i * DP + c);
+          const float4 x1 = make_float4(x0.x + (o.x + bc.x), x0.y + (o.y + bc.y), x0.z + (o.z + bc.z), x0.w + (o.w + bc.w));
+          *reinterpret_cast<float4*>(sx + i * DP + c) = x1;
+          *reinterpret_cast<float4*>(a.xh + ((size_t)b * T + i) * d + c) = x1;
+        }
+      }
+    }
   }
   __syncthreads();
   // ---- 6. LN2 (+ AdaLN modulate) -> split-bf16 operand of c_fc, one warp per row
