@@ -112,6 +112,7 @@ struct MdtHandle {
   float* sk_ws = nullptr; unsigned* sk_cnt = nullptr;
   int cproj_splits = 0;           // MDTB200_CPROJ_SPLITS: 0 = automatic (split-K when the mlp c_proj GEMMs of all chains leave SMs idle), 1..4 fixed
   int cur_chains = 1;             // concurrent sub-batch chains of the call being issued (sample_body)
+  int pdl_late = 1;               // MDTB200_PDL_LATE=0 restores release-at-entry in the SIMT kernels (kernels_simt.cuh, pdl_enter_mode): +0.8 % at B = 256
   __nv_bfloat16 *ka16 = nullptr, *va16 = nullptr; float *gtab = nullptr, *utab = nullptr, *ctab = nullptr;
   size_t cross_rows = 0, ka_layer_stride = 0, tab_layer_stride = 0, ctab_layer_stride = 0;
 
@@ -260,7 +261,7 @@ int launch_ln(MdtHandle* h, const float* x, float* out, __nv_bfloat16* out16, co
               const float* shift, const float* scale, int mod_stride, int M, cudaStream_t st) {
   LnArgs a{};
   a.x = x; a.out = out; a.out16 = out16; a.ld16 = 2 * h->d; a.lo_off = h->d; a.w = w; a.b = b; a.shift = shift; a.scale = scale;
-  a.mod_stride = mod_stride; a.rows_per_group = h->T; a.M = M; a.d = h->d;
+  a.mod_stride = mod_stride; a.rows_per_group = h->T; a.M = M; a.d = h->d; a.late = h->pdl_late;
   int blocks = (M * 32 + 255) / 256;
   switch (h->d / 128) {
     case 1: launch_pdl(ln_mod_kernel<1>, dim3(blocks), dim3(256), 0, st, a); break;
@@ -280,7 +281,7 @@ int launch_attn(MdtHandle* h, const float* q, int ldq, const float* k, const flo
   AttnArgs a{};
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.y = y; a.ldy = h->d; a.y16 = y16; a.ld16 = 2 * h->d; a.lo_off = h->d;
   a.B = B; a.H = h->H; a.hd = h->hd; a.Tq = Tq; a.Tk = Tk; a.causal = causal;
-  a.scale = 1.0f / sqrtf((float)h->hd);
+  a.scale = 1.0f / sqrtf((float)h->hd); a.late = h->pdl_late;
   // shipped shapes run the compile-time specialised kernel (2 heads per CTA); anything else the generic one
   const bool c = causal != 0;
   #define ATT_CASE(HD, TQ, TK, CA)                                                                                  \
@@ -506,7 +507,7 @@ int decoder_eval(MdtHandle* h, const Work& k, const float* x_in, const float* mo
       ca.a16 = k.a16; ca.ld16 = 2 * d; ca.lo_off = d; ca.B = B; ca.T = T; ca.Tc = Tc; ca.H = h->H; ca.d = d;
       {   // the predecessor is the tcgen05 O GEMM (cross_fused implies the tensor-core path): tables / parameters may be read early
         static const int early = getenv("MDTB200_CROSS_EARLY") ? atoi(getenv("MDTB200_CROSS_EARLY")) : 1;
-        ca.early = tcp && early;
+        ca.early = tcp && early; ca.late = h->pdl_late;
       }
       const size_t smem = cross_row_smem_bytes(d, T, Tc, h->H);
       if (d == 384) launch_pdl(cross_row_kernel<3>, dim3(B), dim3(CR_THREADS), smem, st, ca);
@@ -1136,6 +1137,7 @@ MDTB200_API int mdtb200_create(const MdtConfig* cfg, MdtHandle** out) {
   }
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { fail(h, MDTB200_ECUDA, "event creation failed"); return bail(MDTB200_ECUDA); }
   if (const char* e = getenv("MDTB200_BRANCHES")) h->branches = atoi(e);
+  if (const char* e = getenv("MDTB200_PDL_LATE")) h->pdl_late = atoi(e) != 0;
   if (cfg->precision == MDTB200_PREC_BF16X3) {
     if (const char* e = getenv("MDTB200_CPROJ_SPLITS")) h->cproj_splits = atoi(e);
     if (h->cproj_splits < 0 || h->cproj_splits > MdtHandle::SK_MAX_SPLITS) h->cproj_splits = 0;

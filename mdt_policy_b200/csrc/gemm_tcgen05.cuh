@@ -192,7 +192,8 @@ struct SmemLayout {
   static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);      // power of two >= BN
   static constexpr int MIN_CTAS = 1;
   static constexpr int BAR_OFF = STAGES * STAGE;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;         // barriers + tmem slot, + slack for 1024-B alignment
+  static constexpr int BIAS_OFF = BAR_OFF + 256;             // BN floats: this tile's bias slice (staged in the prologue)
+  static constexpr int TOTAL = BIAS_OFF + 1024 + 1024;       // barriers + tmem slot, bias, + slack for 1024-B alignment
 };
 
 // ------------------------------------------------------------------------------------------ the kernel
@@ -248,6 +249,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
+  // static weights (w_early) come with a static bias: its slice is staged in shared memory here, before the dependency wait, so the
+  // epilogue does not pay an L2 round trip after the last MMA
+  float* sbias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+  const bool bias_staged = p.w_early && p.bias && splits <= 1;
+  if (bias_staged && threadIdx.x >= 128 && threadIdx.x < 128 + BN) sbias[threadIdx.x - 128] = p.bias[n0 + threadIdx.x - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -326,10 +332,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int GPR = BN / 8;                            // 8-column groups per row (phase B work items)
     constexpr int ITEMS = BM * GPR / NT;              // phase-B items per thread: 2 (BN = 64) or 4 (BN = 128)
     // residual / gate operands of phase B are fetched now, while the mainloop is still running (this hides their L2
-    // latency, ~1 us); only the BN = 64 instantiation does it, the N >= 1024 GEMMs have no residual epilogue
-    float4 pre_r[BN == 64 ? ITEMS * 2 : 1], pre_g[BN == 64 ? ITEMS * 2 : 1];
-    const bool prefetched = BN == 64 && (p.epi == EPI_RES || p.epi == EPI_RES_GATE) && warp >= 2;
-    if (BN == 64 && prefetched) {
+    // latency, ~1 us); the BN = 64 and the lean BN = 128 instantiations do it (d-wide outputs), the 192-wide / training ones do not
+    constexpr bool PRE = BN == 64 || (BN == 128 && !EXT);
+    float4 pre_r[PRE ? ITEMS * 2 : 1], pre_g[PRE ? ITEMS * 2 : 1];
+    const bool prefetched = PRE && (p.epi == EPI_RES || p.epi == EPI_RES_GATE) && warp >= 2;
+    if (PRE && prefetched) {
 #pragma unroll
       for (int it = 0; it < ITEMS; ++it) {
         const int idx = threadIdx.x + it * NT;
@@ -368,7 +375,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.bias && splits <= 1) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + col + j);
+            float4 b = bias_staged ? *reinterpret_cast<const float4*>(sbias + col + j) : *reinterpret_cast<const float4*>(p.bias + n0 + col + j);
             o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
           }
         }
@@ -451,9 +458,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.epi == EPI_RES || p.epi == EPI_RES_GATE) {
         float4 r0, r1, g0, g1;
-        if (BN == 64 && prefetched) {
-          r0 = pre_r[(BN == 64 ? it : 0) * 2]; r1 = pre_r[(BN == 64 ? it : 0) * 2 + 1];
-          g0 = pre_g[(BN == 64 ? it : 0) * 2]; g1 = pre_g[(BN == 64 ? it : 0) * 2 + 1];
+        if (PRE && prefetched) {
+          r0 = pre_r[(PRE ? it : 0) * 2]; r1 = pre_r[(PRE ? it : 0) * 2 + 1];
+          g0 = pre_g[(PRE ? it : 0) * 2]; g1 = pre_g[(PRE ? it : 0) * 2 + 1];
         } else {
           const float* rr = p.R + (size_t)row * p.ldr + nb;
           r0 = *reinterpret_cast<const float4*>(rr); r1 = *reinterpret_cast<const float4*>(rr + 4);

@@ -55,6 +55,10 @@ __device__ __forceinline__ void ktrace(int tag, int event) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait(int tag = KT_OTHER) { asm volatile("griddepcontrol.wait;" ::: "memory"); ktrace(tag, 0); }
 __device__ __forceinline__ void pdl_enter(int tag = KT_OTHER) { pdl_trigger(); pdl_wait(tag); }
+// late = 1: the dependents are released by a later pdl_trigger() in the kernel body instead of at entry.  A dependent tcgen05 GEMM CTA
+// owns a whole SM from the moment it is resident; released at entry it idles through this kernel's own dependency wait and body, which
+// costs SM time once several sub-batch chains compete for the SMs (it only needs ~1.5 us of lead for its prologue).
+__device__ __forceinline__ void pdl_enter_mode(int tag, int late) { if (!late) pdl_trigger(); pdl_wait(tag); }
 
 // ------------------------------------------------------------------------------------------
 // activations (exact variants, matching ATen)
@@ -277,11 +281,13 @@ struct LnArgs {
   const float* shift; const float* scale;    // may be null (plain LN)
   int mod_stride; int rows_per_group;
   int M, d;
+  int late;                                  // PDL: release the dependents after the own dependency wait (pdl_enter_mode)
 };
 
 template <int VPL>   // float4 vectors per lane: d = 128 * VPL
 __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
-  pdl_enter(KT_LN);
+  pdl_enter_mode(KT_LN, a.late);
+  if (a.late) pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const float* xr = a.x + (size_t)warp * a.d;
@@ -341,6 +347,7 @@ struct AttnArgs {
   int B, H, hd, Tq, Tk, causal;
   float scale;
   float p_drop; unsigned long long seed;      // training only: dropout on the attention probabilities (generic kernel)
+  int late;                                   // PDL: release the dependents after the scores (specialised kernel; pdl_enter_mode)
 };
 
 // counter-based uniform in [0,1): splitmix64 of (seed, element index).  Forward and backward regenerate the same mask.
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(128) attention_fixed_kernel(AttnArgs a) {
   __shared__ __align__(16) float sk[TK * DP];
   __shared__ __align__(16) float sv[TK * DP];
   __shared__ float sp[HC * TQ * (TK + 1)];
-  pdl_enter(KT_ATTN);
+  pdl_enter_mode(KT_ATTN, a.late);
   const int b = blockIdx.x, c0 = blockIdx.y * DC, tid = threadIdx.x;
 #pragma unroll
   for (int e = tid; e < TQ * D4; e += NT) {
@@ -477,6 +484,7 @@ __global__ void __launch_bounds__(128) attention_fixed_kernel(AttnArgs a) {
     sp[(h * TQ + i) * (TK + 1) + j] = s;
   }
   __syncthreads();
+  if (a.late) pdl_trigger();
   if (tid < HC * TQ) {
     float* row = sp + tid * (TK + 1);
     float mx = -INFINITY;
@@ -592,6 +600,7 @@ struct CrossRowArgs {
   __nv_bfloat16* a16; int ld16, lo_off;        // LN2 (+modulate) output: split-bf16 operand of c_fc
   int B, T, Tc, H, d;
   int early;                                   // 1: tables / parameters are requested BEFORE the dependency wait (see the kernel)
+  int late;                                    // PDL: release the dependents after the softmax instead of at entry (pdl_enter_mode)
 };
 constexpr int CR_THREADS = 384;
 constexpr int CR_TMAX = 12;                    // score accumulators per thread (T * 32 < CR_THREADS -> T <= 11)
@@ -636,7 +645,7 @@ __global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
   float* sct = spart + C::KSL * T * HT;
   float* sprm = sct + ((HT + 3) & ~3);   // bco | ln2_w | ln2_b | shift | scale
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_trigger();
+  if (!a.late) pdl_trigger();
   if (!a.early) pdl_wait(KT_CROSS);
   // ---- 1. every global operand is requested up front: G and U rows (registers), LN3 parameters (one warp per row), the small
   //         parameter vectors and score constants (remaining warps -> shared memory); then (after the wait) the T residual rows
@@ -763,6 +772,7 @@ __global__ void __launch_bounds__(CR_THREADS) cross_row_kernel(CrossRowArgs a) {
     for (int j = 0; j < Tc; ++j) dst[j * C::PS] = expf(row[j] - mx) * inv;
   }
   __syncthreads();
+  if (a.late) pdl_trigger();
   // ---- 5. x_i += sum_hj p_i,hj U_hj + b_co   (kept in shared memory for the LayerNorm below, written back to the residual stream)
   {
     const int c = (tid % D4) * 4, grp = tid / D4;
