@@ -8,7 +8,8 @@ from tests import helpers
 B = 256
 model = helpers.build_product(helpers.mdtv_inner_cfg(), 0, "trained")
 state = {"state_images": torch.randn(B, 2, 384, device="cuda"), "modality": "lang"}
-model(state, torch.randn(B, 10, 7, device="cuda"), torch.randn(B, 1, 512, device="cuda"), torch.ones(B, device="cuda"))
+with torch.no_grad():     # the inference engine (with grad enabled the call would take the training path and create no engine)
+    model(state, torch.randn(B, 10, 7, device="cuda"), torch.randn(B, 1, 512, device="cuda"), torch.ones(B, device="cuda"))
 eng = list(model.inner_model._engines.values())[0]
 M, d = 640, 384
 for m, n, k, epi in ((M, 3 * d, d, 0), (M, d, d, 5), (M, 4 * d, d, 1), (M, d, 4 * d, 5)):
